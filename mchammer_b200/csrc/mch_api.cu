@@ -1,0 +1,329 @@
+// mch_api.cu -- extern "C" surface of libmchammer_b200.so (see include/mchammer_b200.h).
+// Host-side work here: argument checks, kernel-variant dispatch, launch geometry, and the
+// numpy-compatible PCG64 seeding.  No device allocation, no synchronisation.
+#include "../../include/mchammer_b200.h"
+
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+
+#include "mch_collapse.cuh"
+#include "mch_device.cuh"
+#include "mch_optimize.cuh"
+#include "mch_potential.cuh"
+
+namespace {
+
+thread_local char g_error[512] = "";
+
+int fail(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_error, sizeof(g_error), fmt, ap);
+  va_end(ap);
+  return code;
+}
+
+constexpr int kMaxSmem = 227 * 1024;
+
+mch::Params to_params(const mch_params& p) {
+  mch::Params q;
+  q.step_size = p.step_size;
+  q.target_bond_length = p.target_bond_length;
+  q.bond_epsilon = p.bond_epsilon;
+  q.nonbond_epsilon = p.nonbond_epsilon;
+  q.nonbond_sigma = p.nonbond_sigma;
+  q.nonbond_mu = p.nonbond_mu;
+  q.beta = p.beta;
+  return q;
+}
+
+// mu == 3 -> cubic fast path; other small positive integers -> square-and-multiply;
+// anything else -> exp2/log2 (fp32) or pow (fp64).
+int mu_kind(double mu, int* mu_int) {
+  *mu_int = 0;
+  if (mu == 3.0) return mch::MU_3;
+  if (mu >= 1.0 && mu <= 64.0 && std::floor(mu) == mu) {
+    *mu_int = (int)mu;
+    return mch::MU_INT;
+  }
+  return mch::MU_REAL;
+}
+
+int auto_threads(int n_atoms) {
+  if (n_atoms <= 128) return 32;
+  if (n_atoms <= 384) return 64;
+  if (n_atoms <= 3072) return 128;
+  return 256;
+}
+
+int check_threads(int requested, int n_atoms, int* out) {
+  int t = requested > 0 ? requested : auto_threads(n_atoms);
+  if (t % 32 != 0 || t < 32 || t > 256) return fail(MCH_ERR_INVALID, "threads must be a multiple of 32 in [32, 256], got %d", t);
+  *out = t;
+  return MCH_OK;
+}
+
+template <typename K, typename A>
+int launch(K kernel, const A& args, int blocks, int threads, int smem, cudaStream_t stream, const char* what) {
+  cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  if (e != cudaSuccess) return fail(MCH_ERR_CUDA, "%s: cudaFuncSetAttribute(%d B): %s", what, smem, cudaGetErrorString(e));
+  kernel<<<blocks, threads, smem, stream>>>(args);
+  e = cudaGetLastError();
+  if (e != cudaSuccess) return fail(MCH_ERR_CUDA, "%s: launch failed: %s", what, cudaGetErrorString(e));
+  return MCH_OK;
+}
+
+// dispatch helpers: compute type x io type x mu kind
+template <typename T, typename Tio>
+int launch_optimize_mu(int mk, const mch::OptArgs& a, int threads, int smem, cudaStream_t s) {
+  switch (mk) {
+    case mch::MU_3: return launch(mch::mch_optimize_kernel<T, Tio, mch::MU_3>, a, a.C, threads, smem, s, "mch_optimize_batch");
+    case mch::MU_INT: return launch(mch::mch_optimize_kernel<T, Tio, mch::MU_INT>, a, a.C, threads, smem, s, "mch_optimize_batch");
+    default: return launch(mch::mch_optimize_kernel<T, Tio, mch::MU_REAL>, a, a.C, threads, smem, s, "mch_optimize_batch");
+  }
+}
+
+template <typename T, typename Tio>
+int launch_potential_mu(int mk, const mch::PotArgs& a, int threads, int smem, cudaStream_t s) {
+  switch (mk) {
+    case mch::MU_3: return launch(mch::mch_potential_kernel<T, Tio, mch::MU_3>, a, a.C, threads, smem, s, "mch_potential_batch");
+    case mch::MU_INT: return launch(mch::mch_potential_kernel<T, Tio, mch::MU_INT>, a, a.C, threads, smem, s, "mch_potential_batch");
+    default: return launch(mch::mch_potential_kernel<T, Tio, mch::MU_REAL>, a, a.C, threads, smem, s, "mch_potential_batch");
+  }
+}
+
+bool dtype_ok(int d) { return d == MCH_F64 || d == MCH_F32; }
+
+// ------------------------------------------------------------------ arithmetic probes
+template <typename T>
+__global__ void probe_fma_kernel(int iters, float* sink) {
+  T a0 = (T)threadIdx.x * (T)1e-3, a1 = a0 + (T)1, a2 = a0 + (T)2, a3 = a0 + (T)3;
+  T a4 = a0 + (T)4, a5 = a0 + (T)5, a6 = a0 + (T)6, a7 = a0 + (T)7;
+  const T m = (T)0.999, c = (T)1e-3;
+  for (int i = 0; i < iters; ++i) {
+    a0 = fma(a0, m, c); a1 = fma(a1, m, c); a2 = fma(a2, m, c); a3 = fma(a3, m, c);
+    a4 = fma(a4, m, c); a5 = fma(a5, m, c); a6 = fma(a6, m, c); a7 = fma(a7, m, c);
+  }
+  const T r = ((a0 + a1) + (a2 + a3)) + ((a4 + a5) + (a6 + a7));
+  if (r == (T)-12345.678) *sink = (float)r;  // never true; keeps the loop alive
+}
+
+__global__ void probe_rsqrt_kernel(int iters, float* sink) {
+  float a0 = 1.0f + threadIdx.x, a1 = a0 + 1.f, a2 = a0 + 2.f, a3 = a0 + 3.f;
+  float a4 = a0 + 4.f, a5 = a0 + 5.f, a6 = a0 + 6.f, a7 = a0 + 7.f;
+  for (int i = 0; i < iters; ++i) {
+    a0 = rsqrtf(a0); a1 = rsqrtf(a1); a2 = rsqrtf(a2); a3 = rsqrtf(a3);
+    a4 = rsqrtf(a4); a5 = rsqrtf(a5); a6 = rsqrtf(a6); a7 = rsqrtf(a7);
+  }
+  const float r = ((a0 + a1) + (a2 + a3)) + ((a4 + a5) + (a6 + a7));
+  if (r == -12345.678f) *sink = r;
+}
+
+// ------------------------------------------------------------------ numpy SeedSequence
+// Published algorithm (numpy/random/bit_generator.pyx, after M.E. O'Neill's seed_seq_fe):
+// 4-word uint32 pool, hashmix/mix, then generate_state; PCG64 takes 4 uint64 = 8 words.
+void seed_sequence_8(uint64_t seed, uint32_t out[8]) {
+  const uint32_t XSHIFT = 16, INIT_A = 0x43b0d7e5u, MULT_A = 0x931e8875u;
+  const uint32_t INIT_B = 0x8b51f9ddu, MULT_B = 0x58f38dedu;
+  const uint32_t MIX_L = 0xca01f9ddu, MIX_R = 0x4973f715u;
+  uint32_t entropy[2] = {(uint32_t)seed, (uint32_t)(seed >> 32)};
+  const int n_entropy = entropy[1] != 0 ? 2 : 1;  // numpy drops leading zero words (0 -> [0])
+  uint32_t hash_const = INIT_A;
+  auto hashmix = [&](uint32_t v) {
+    v ^= hash_const;
+    hash_const *= MULT_A;
+    v *= hash_const;
+    v ^= v >> XSHIFT;
+    return v;
+  };
+  auto mix = [&](uint32_t x, uint32_t y) {
+    uint32_t r = MIX_L * x - MIX_R * y;
+    r ^= r >> XSHIFT;
+    return r;
+  };
+  uint32_t pool[4];
+  for (int i = 0; i < 4; ++i) pool[i] = hashmix(i < n_entropy ? entropy[i] : 0u);
+  for (int src = 0; src < 4; ++src)
+    for (int dst = 0; dst < 4; ++dst)
+      if (src != dst) pool[dst] = mix(pool[dst], hashmix(pool[src]));
+  uint32_t hc = INIT_B;
+  for (int i = 0; i < 8; ++i) {
+    uint32_t v = pool[i & 3];
+    v ^= hc;
+    hc *= MULT_B;
+    v *= hc;
+    v ^= v >> XSHIFT;
+    out[i] = v;
+  }
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* mch_last_error(void) { return g_error; }
+int mch_version(void) { return 100; }
+
+int mch_optimize_smem_bytes(int n_atoms, int n_subunits, int n_bonds, int max_subunit_atoms, int compute_dtype) {
+  if (n_atoms <= 0 || n_subunits <= 0 || n_bonds < 0 || max_subunit_atoms <= 0 || !dtype_ok(compute_dtype))
+    return fail(MCH_ERR_INVALID, "mch_optimize_smem_bytes: bad sizes");
+  const long long est = 4LL * n_atoms * 8 + 8LL * n_subunits * n_subunits;
+  if (est > (1LL << 30)) return fail(MCH_ERR_TOO_LARGE, "molecule too large");
+  const mch::OptLayout L = mch::opt_layout(n_atoms, n_subunits, n_bonds, max_subunit_atoms, compute_dtype == MCH_F64 ? 8 : 4);
+  if (L.total > kMaxSmem) return fail(MCH_ERR_TOO_LARGE, "chain needs %d B of shared memory (limit %d)", L.total, kMaxSmem);
+  return L.total;
+}
+
+int mch_optimize_batch(const mch_optimize_desc* d, void* stream) {
+  if (!d) return fail(MCH_ERR_INVALID, "mch_optimize_batch: null descriptor");
+  if (d->n_chains <= 0 || d->n_atoms <= 0 || d->n_subunits <= 0 || d->n_bonds <= 0 || d->max_subunit_atoms <= 0)
+    return fail(MCH_ERR_INVALID, "mch_optimize_batch: sizes must be positive (chains %d atoms %d subunits %d bonds %d max_su %d)",
+                d->n_chains, d->n_atoms, d->n_subunits, d->n_bonds, d->max_subunit_atoms);
+  if (d->n_bonds > 65535 || d->n_subunits > 8191)
+    return fail(MCH_ERR_INVALID, "mch_optimize_batch: at most 65535 bonds and 8191 subunits");
+  if (!dtype_ok(d->io_dtype) || !dtype_ok(d->compute_dtype)) return fail(MCH_ERR_INVALID, "mch_optimize_batch: unknown dtype");
+  if (!d->pos_in || !d->pos_out || !d->perm || !d->su_offsets || !d->bonds || !d->bond_su || !d->rng_state ||
+      !d->system_potential || !d->nonbonded_potential || !d->max_bond_distance || !d->n_accepted || !d->last_step_info)
+    return fail(MCH_ERR_INVALID, "mch_optimize_batch: null required pointer");
+  int threads;
+  int rc = check_threads(d->threads_per_chain, d->n_atoms, &threads);
+  if (rc != MCH_OK) return rc;
+  const int smem = mch_optimize_smem_bytes(d->n_atoms, d->n_subunits, d->n_bonds, d->max_subunit_atoms, d->compute_dtype);
+  if (smem < 0) return smem;
+
+  mch::OptArgs a;
+  a.pos_in = d->pos_in; a.pos_in_stride = d->pos_in_chain_stride; a.pos_out = d->pos_out;
+  a.C = d->n_chains; a.N = d->n_atoms; a.S = d->n_subunits; a.B = d->n_bonds; a.max_su = d->max_subunit_atoms;
+  a.perm = d->perm; a.su_off = d->su_offsets; a.bonds = d->bonds; a.bond_su = d->bond_su;
+  a.p = to_params(d->params);
+  const int mk = mu_kind(d->params.nonbond_mu, &a.mu_int);
+  a.num_steps = d->num_steps < 1 ? 1 : d->num_steps;
+  a.rng = d->rng_state;
+  a.U = d->system_potential; a.Unb = d->nonbonded_potential; a.maxd = d->max_bond_distance;
+  a.n_accept = d->n_accepted; a.last_info = d->last_step_info;
+  a.trace_f = d->trace_potentials; a.trace_i = d->trace_info; a.traj = d->trajectory;
+  a.pairs = reinterpret_cast<unsigned long long*>(d->pair_evals);
+  a.inexact_undo = d->inexact_undo;
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  if (d->compute_dtype == MCH_F64) {
+    return d->io_dtype == MCH_F64 ? launch_optimize_mu<double, double>(mk, a, threads, smem, s)
+                                  : launch_optimize_mu<double, float>(mk, a, threads, smem, s);
+  }
+  return d->io_dtype == MCH_F64 ? launch_optimize_mu<float, double>(mk, a, threads, smem, s)
+                                : launch_optimize_mu<float, float>(mk, a, threads, smem, s);
+}
+
+int mch_potential_batch(const void* pos, int io_dtype, int compute_dtype, int n_mol, int n_atoms,
+                        const int32_t* bonds, int n_bonds, const mch_params* params,
+                        double* system_potential, double* nonbonded_potential,
+                        double* max_bond_distance, void* stream) {
+  if (!pos || !params || !system_potential || !nonbonded_potential || !max_bond_distance)
+    return fail(MCH_ERR_INVALID, "mch_potential_batch: null required pointer");
+  if (n_mol <= 0 || n_atoms <= 0 || n_bonds < 0 || (n_bonds > 0 && !bonds))
+    return fail(MCH_ERR_INVALID, "mch_potential_batch: bad sizes");
+  if (!dtype_ok(io_dtype) || !dtype_ok(compute_dtype)) return fail(MCH_ERR_INVALID, "mch_potential_batch: unknown dtype");
+  if (n_atoms > (1 << 20)) return fail(MCH_ERR_TOO_LARGE, "molecule too large");
+  const mch::PotLayout L = mch::pot_layout(n_atoms, compute_dtype == MCH_F64 ? 8 : 4);
+  if (L.total > kMaxSmem) return fail(MCH_ERR_TOO_LARGE, "molecule needs %d B of shared memory (limit %d)", L.total, kMaxSmem);
+  mch::PotArgs a;
+  a.pos = pos; a.C = n_mol; a.N = n_atoms; a.B = n_bonds; a.bonds = bonds;
+  a.p = to_params(*params);
+  const int mk = mu_kind(params->nonbond_mu, &a.mu_int);
+  a.U = system_potential; a.Unb = nonbonded_potential; a.maxd = max_bond_distance;
+  const int threads = n_atoms <= 64 ? 32 : (n_atoms <= 256 ? 64 : (n_atoms <= 1024 ? 128 : 256));
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  if (compute_dtype == MCH_F64) {
+    return io_dtype == MCH_F64 ? launch_potential_mu<double, double>(mk, a, threads, L.total, s)
+                               : launch_potential_mu<double, float>(mk, a, threads, L.total, s);
+  }
+  return io_dtype == MCH_F64 ? launch_potential_mu<float, double>(mk, a, threads, L.total, s)
+                             : launch_potential_mu<float, float>(mk, a, threads, L.total, s);
+}
+
+int mch_collapse_batch(const mch_collapse_desc* d, void* stream) {
+  if (!d) return fail(MCH_ERR_INVALID, "mch_collapse_batch: null descriptor");
+  if (d->n_mol <= 0 || d->n_atoms <= 0 || d->n_subunits <= 0 || d->n_bonds < 0 || d->max_steps < 0)
+    return fail(MCH_ERR_INVALID, "mch_collapse_batch: bad sizes");
+  if (!dtype_ok(d->io_dtype) || !dtype_ok(d->compute_dtype)) return fail(MCH_ERR_INVALID, "mch_collapse_batch: unknown dtype");
+  if (!d->pos_in || !d->pos_out || !d->perm || !d->su_offsets || !d->n_heavy || (d->n_bonds > 0 && !d->bonds) ||
+      !d->steps_run || !d->min_distance || !d->max_bond_distance || !d->status)
+    return fail(MCH_ERR_INVALID, "mch_collapse_batch: null required pointer");
+  if ((d->trace_max_bond || d->trajectory) && d->trace_capacity <= 0)
+    return fail(MCH_ERR_INVALID, "mch_collapse_batch: trace buffers need trace_capacity > 0");
+  if (d->n_atoms > (1 << 20) || d->n_subunits > (1 << 16)) return fail(MCH_ERR_TOO_LARGE, "molecule too large");
+  int threads;
+  int rc = check_threads(d->threads_per_mol, d->n_atoms, &threads);
+  if (rc != MCH_OK) return rc;
+  const mch::ColLayout L = mch::col_layout(d->n_atoms, d->n_subunits, d->n_bonds, d->compute_dtype == MCH_F64 ? 8 : 4);
+  if (L.total > kMaxSmem) return fail(MCH_ERR_TOO_LARGE, "molecule needs %d B of shared memory (limit %d)", L.total, kMaxSmem);
+  mch::ColArgs a;
+  a.pos_in = d->pos_in; a.pos_in_stride = d->pos_in_mol_stride; a.pos_out = d->pos_out;
+  a.C = d->n_mol; a.N = d->n_atoms; a.S = d->n_subunits; a.B = d->n_bonds;
+  a.perm = d->perm; a.su_off = d->su_offsets; a.n_heavy = d->n_heavy; a.bonds = d->bonds;
+  a.step_size = d->step_size; a.threshold = d->distance_threshold; a.scale_steps = d->scale_steps;
+  a.max_steps = d->max_steps;
+  a.steps_run = d->steps_run; a.min_dist = d->min_distance; a.maxd_last = d->max_bond_distance; a.status = d->status;
+  a.trace_maxd = d->trace_max_bond; a.traj = d->trajectory; a.trace_cap = d->trace_capacity;
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  if (d->compute_dtype == MCH_F64) {
+    return d->io_dtype == MCH_F64
+               ? launch(mch::mch_collapse_kernel<double, double>, a, a.C, threads, L.total, s, "mch_collapse_batch")
+               : launch(mch::mch_collapse_kernel<double, float>, a, a.C, threads, L.total, s, "mch_collapse_batch");
+  }
+  return d->io_dtype == MCH_F64
+             ? launch(mch::mch_collapse_kernel<float, double>, a, a.C, threads, L.total, s, "mch_collapse_batch")
+             : launch(mch::mch_collapse_kernel<float, float>, a, a.C, threads, L.total, s, "mch_collapse_batch");
+}
+
+int mch_pcg64_seed(const uint64_t* seeds, int n, uint64_t* out) {
+  if (!seeds || !out || n < 0) return fail(MCH_ERR_INVALID, "mch_pcg64_seed: bad arguments");
+  for (int k = 0; k < n; ++k) {
+    uint32_t w[8];
+    seed_sequence_8(seeds[k], w);
+    uint64_t v[4];
+    for (int i = 0; i < 4; ++i) v[i] = (uint64_t)w[2 * i] | ((uint64_t)w[2 * i + 1] << 32);
+    // pcg_setseq_128_srandom_r(initstate = v0:v1, initseq = v2:v3)
+    mch::Pcg64 g;
+    g.inc_hi = (v[2] << 1) | (v[3] >> 63);
+    g.inc_lo = (v[3] << 1) | 1ULL;
+    g.hi = 0; g.lo = 0; g.has32 = 0; g.half = 0;
+    mch::pcg_advance(g);
+    const uint64_t lo = g.lo + v[1];
+    g.hi = g.hi + v[0] + (lo < g.lo ? 1ULL : 0ULL);
+    g.lo = lo;
+    mch::pcg_advance(g);
+    mch::pcg_store(g, out + 6LL * k);
+  }
+  return MCH_OK;
+}
+
+int mch_pcg64_stream_check(uint64_t* rng_state, int rounds, uint32_t bound, int64_t* ints_out, double* doubles_out) {
+  if (!rng_state || !ints_out || !doubles_out || rounds < 0 || bound == 0) return fail(MCH_ERR_INVALID, "mch_pcg64_stream_check: bad arguments");
+  mch::Pcg64 g = mch::pcg_load(rng_state);
+  int ni = 0, nd = 0;
+  for (int k = 0; k < rounds; ++k) {
+    ints_out[ni++] = mch::pcg_bounded(g, bound);
+    ints_out[ni++] = mch::pcg_bounded(g, 2u);
+    doubles_out[nd++] = mch::pcg_double(g);
+    ints_out[ni++] = mch::pcg_bounded(g, 2u);
+    if (k % 3 == 0) doubles_out[nd++] = mch::pcg_double(g);
+  }
+  mch::pcg_store(g, rng_state);
+  return MCH_OK;
+}
+
+int mch_probe_fma(int dtype, int blocks, int threads, int iters, float* sink, void* stream) {
+  if (blocks <= 0 || threads <= 0 || threads > 1024 || iters <= 0 || !sink) return fail(MCH_ERR_INVALID, "mch_probe_fma: bad arguments");
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  if (dtype == MCH_F64) probe_fma_kernel<double><<<blocks, threads, 0, s>>>(iters, sink);
+  else if (dtype == MCH_F32) probe_fma_kernel<float><<<blocks, threads, 0, s>>>(iters, sink);
+  else if (dtype == 2) probe_rsqrt_kernel<<<blocks, threads, 0, s>>>(iters, sink);
+  else return fail(MCH_ERR_INVALID, "mch_probe_fma: dtype must be 0 (f64 fma), 1 (f32 fma) or 2 (f32 rsqrt)");
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return fail(MCH_ERR_CUDA, "mch_probe_fma: %s", cudaGetErrorString(e));
+  return MCH_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,394 @@
+// mch_optimize.cuh -- the resident Metropolis kernel: ONE CTA owns ONE chain for all steps.
+//
+// Replaces, per chain, the reference loop
+//     Optimizer.get_result / get_trajectory   (optimizer.py:308-438)
+//       _run_first_step                       (optimizer.py:164-200)
+//       _run_step                             (optimizer.py:202-306)
+//         translate_atoms_along_vector        (mc_operations.py:15-28)
+//         compute_potential                   (optimizer.py:122-142)
+//         test_move                           (mc_operations.py:39-52)
+//
+// Data layout
+//   HBM   : positions [C][N][3] (io dtype, caller's atom order), rng_state [C][6] u64,
+//           topology arrays shared by all chains (perm, su_offsets, bonds, bond_su).
+//   SMEM  : the chain's atoms as SoA X/Y/Z in *slot* order (atoms permuted so that every
+//           subunit is a contiguous slot range), the displaced rows Q of the moving
+//           subunit, per-column sums, the S x S table E of subunit-pair energies,
+//           per-subunit coordinate sums.  Nothing goes back to HBM between steps except
+//           the optional trace/trajectory records.
+//
+// Algorithm per step (exact reference order of random draws)
+//   control warp : draws -> translation vector -> Q = P[ms] - tv -> bond energies of the
+//                  trial geometry
+//   all warps    : sum_{i in ms, j not in ms} r_ij^-mu   (pair_sweep; n_ms x (N - n_ms))
+//   control warp : dU_nb = eps sigma^mu * sum - sum_t E[ms][t];  Metropolis test;
+//                  accept -> P[ms] = Q, refresh row/column ms of E from the per-column
+//                  sums;  reject -> P untouched (fp32) or the reference's inexact undo
+//                  (p - v) + v (fp64 parity mode, optimizer.py:269-277).
+//   Intra-subunit pairs are constant under rigid moves; they are evaluated once at step 0
+//   and carried in U_nb (the reference re-sums them every step, optimizer.py:114-120).
+#pragma once
+
+#include "mch_device.cuh"
+
+namespace mch {
+
+struct OptArgs {
+  const void* pos_in;        // [C or 1][N][3] io dtype
+  long long pos_in_stride;   // elements between chains (0: every chain starts from chain 0)
+  void* pos_out;             // [C][N][3] io dtype
+  int C, N, S, B;
+  int max_su;                // largest subunit (atoms)
+  const int* perm;           // [N] slot -> atom id
+  const int* su_off;         // [S+1] slot offsets
+  const int* bonds;          // [B][2] atom ids, caller's order inside each pair
+  const int* bond_su;        // [B][2] subunit (position in dict order) of each bond end
+  Params p;
+  int mu_int;
+  int num_steps;             // counts step 0, like the reference
+  uint64_t* rng;             // [C][6] in/out
+  double* U;                 // [C] out
+  double* Unb;               // [C] out
+  double* maxd;              // [C] out
+  int* n_accept;             // [C] out
+  int* last_info;            // [C] out: trace word of the last step
+  double* trace_f;           // [C][num_steps][3] or null: U, U_nb, max bond distance
+  int* trace_i;              // [C][num_steps] or null: bond | passed<<16 | kind<<17 | ms<<18
+  void* traj;                // [C][num_steps][N][3] io dtype or null
+  unsigned long long* pairs; // [C] or null: pair terms evaluated
+  int inexact_undo;          // 1: reproduce (p - v) + v on reject (fp64 parity)
+};
+
+// Shared-memory carve-up, identical on host (size query) and device.
+struct OptLayout {
+  int x, y, z, colsum, rows, E, csum, wsum, suoff, bslot, bsu, ctl, total;
+};
+
+MCH_HD int align_up(int v, int a) { return (v + a - 1) / a * a; }
+
+MCH_HD OptLayout opt_layout(int N, int S, int B, int max_su, int tsize) {
+  OptLayout L;
+  const int np = align_up(N, 8);
+  int o = 0;
+  L.x = o; o += np * tsize;
+  L.y = o; o += np * tsize;
+  L.z = o; o += np * tsize;
+  L.colsum = o; o += np * (tsize < 4 ? 4 : tsize);
+  o = align_up(o, 32);
+  L.rows = o; o += align_up(max_su, 2) * 4 * tsize;
+  o = align_up(o, 16);
+  L.E = o; o += S * S * 8;
+  L.csum = o; o += S * 3 * 8;
+  L.wsum = o; o += 3 * 32 * 8;
+  L.suoff = o; o += align_up(S + 1, 4) * 4;
+  L.bslot = o; o += align_up(2 * B, 4) * 4;
+  L.bsu = o; o += align_up(2 * B, 4) * 4;
+  L.ctl = o; o += 64;
+  L.total = align_up(o, 16);
+  return L;
+}
+
+struct Ctl {
+  int nrows;
+  int c0, g0, g1, c1;
+  int ms;
+};
+
+#ifdef __CUDACC__
+
+template <typename Tio> MCH_D double load_io(const void* base, long long idx) {
+  return (double)reinterpret_cast<const Tio*>(base)[idx];
+}
+template <typename Tio> MCH_D void store_io(void* base, long long idx, double v) {
+  reinterpret_cast<Tio*>(base)[idx] = (Tio)v;
+}
+
+template <typename T, typename Tio, int MUK>
+__global__ void __launch_bounds__(256)
+mch_optimize_kernel(const __grid_constant__ OptArgs a) {
+  extern __shared__ __align__(32) unsigned char smem[];
+  const int c = blockIdx.x;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int nt = blockDim.x, nwarps = nt >> 5;
+  const int N = a.N, S = a.S, B = a.B;
+
+  const OptLayout L = opt_layout(N, S, B, a.max_su, (int)sizeof(T));
+  T* X = reinterpret_cast<T*>(smem + L.x);
+  T* Y = reinterpret_cast<T*>(smem + L.y);
+  T* Z = reinterpret_cast<T*>(smem + L.z);
+  T* colsum = reinterpret_cast<T*>(smem + L.colsum);
+  Row4<T>* Q = reinterpret_cast<Row4<T>*>(smem + L.rows);
+  double* E = reinterpret_cast<double*>(smem + L.E);
+  double* csum = reinterpret_cast<double*>(smem + L.csum);
+  double* wsum = reinterpret_cast<double*>(smem + L.wsum);   // 3 x 32: [0..31] cross, [32..63] intra
+  int* suoff = reinterpret_cast<int*>(smem + L.suoff);
+  int* bslot = reinterpret_cast<int*>(smem + L.bslot);
+  int* bsu = reinterpret_cast<int*>(smem + L.bsu);
+  Ctl* ctl = reinterpret_cast<Ctl*>(smem + L.ctl);
+
+  const PairTerm<T, MUK> term(a.p.nonbond_mu, a.mu_int);
+  const double scale = a.p.nonbond_epsilon * pow(a.p.nonbond_sigma, a.p.nonbond_mu);
+
+  // ---------------------------------------------------------------- prologue
+  // inverse permutation (atom id -> slot) in the colsum scratch, then bonds in slot space
+  int* inv = reinterpret_cast<int*>(colsum);
+  for (int n = tid; n < N; n += nt) inv[a.perm[n]] = n;
+  for (int s = tid; s <= S; s += nt) suoff[s] = a.su_off[s];
+  __syncthreads();
+  for (int k = tid; k < 2 * B; k += nt) {
+    bslot[k] = inv[a.bonds[k]];
+    bsu[k] = a.bond_su[k];
+  }
+  const long long in_base = (long long)c * a.pos_in_stride;
+  // fp32 compute works in a frame centred on the start geometry (translation invariant
+  // path; keeps |coordinates| small).  fp64 keeps the caller's frame bit for bit.
+  double origin[3] = {0.0, 0.0, 0.0};
+  if (sizeof(T) == 4) {
+    double sx = 0.0, sy = 0.0, sz = 0.0;
+    for (int n = tid; n < N; n += nt) {
+      sx += load_io<Tio>(a.pos_in, in_base + 3LL * n + 0);
+      sy += load_io<Tio>(a.pos_in, in_base + 3LL * n + 1);
+      sz += load_io<Tio>(a.pos_in, in_base + 3LL * n + 2);
+    }
+    sx = warp_sum(sx); sy = warp_sum(sy); sz = warp_sum(sz);
+    __syncthreads();  // inv reads above are done before wsum/colsum reuse below
+    if (lane == 0) { wsum[warp] = sx; wsum[32 + warp] = sy; wsum[64 + warp] = sz; }
+    __syncthreads();
+    for (int w = 0; w < nwarps; ++w) {
+      origin[0] += wsum[w]; origin[1] += wsum[32 + w]; origin[2] += wsum[64 + w];
+    }
+    origin[0] /= N; origin[1] /= N; origin[2] /= N;
+  }
+  __syncthreads();
+  for (int n = tid; n < N; n += nt) {
+    const long long src = in_base + 3LL * a.perm[n];
+    X[n] = (T)(load_io<Tio>(a.pos_in, src + 0) - origin[0]);
+    Y[n] = (T)(load_io<Tio>(a.pos_in, src + 1) - origin[1]);
+    Z[n] = (T)(load_io<Tio>(a.pos_in, src + 2) - origin[2]);
+  }
+  for (int k = tid; k < S * S; k += nt) E[k] = 0.0;
+  __syncthreads();
+
+  // ---------------------------------------------------------------- control-warp state
+  // (uniform across the 32 lanes of warp 0; other warps never read it)
+  Pcg64 rng = pcg_load(a.rng + 6LL * c);
+  double U = 0.0, Unb = 0.0, Ub_trial = 0.0, e_intra = 0.0;
+  T tvx = (T)0, tvy = (T)0, tvz = (T)0;
+  int ms = 0, kb = 0, kind = 0, n_acc = 0, info = -1;
+  unsigned long long pair_count = 0ULL;
+
+  auto fill_rows = [&](int s, T dx, T dy, T dz) {  // Q = P[s] - d ; warp 0 only
+    const int r0 = suoff[s], n = suoff[s + 1] - r0;
+    for (int i = lane; i < n; i += 32) {
+      Row4<T> q;
+      q.x = X[r0 + i] - dx; q.y = Y[r0 + i] - dy; q.z = Z[r0 + i] - dz; q.w = (T)0;
+      Q[i] = q;
+    }
+    return n;
+  };
+  auto refresh_csum = [&](int s) {  // coordinate sums of subunit s from current positions
+    const int r0 = suoff[s], r1 = suoff[s + 1];
+    double sx = 0.0, sy = 0.0, sz = 0.0;
+    for (int i = r0 + lane; i < r1; i += 32) { sx += (double)X[i]; sy += (double)Y[i]; sz += (double)Z[i]; }
+    sx = warp_sum(sx); sy = warp_sum(sy); sz = warp_sum(sz);
+    if (lane == 0) { csum[3 * s] = sx; csum[3 * s + 1] = sy; csum[3 * s + 2] = sz; }
+  };
+  // bond energy sum and longest bond; ends inside subunit `moved` are displaced by -tv
+  auto bond_terms = [&](int moved, T dx, T dy, T dz, double& longest) {
+    const int m0 = moved >= 0 ? suoff[moved] : -1, m1 = moved >= 0 ? suoff[moved + 1] : -1;
+    double e = 0.0, far = 0.0;
+    for (int b = lane; b < B; b += 32) {
+      const int sa = bslot[2 * b], sb = bslot[2 * b + 1];
+      const bool ma = sa >= m0 && sa < m1, mb = sb >= m0 && sb < m1;
+      const T ax = ma ? X[sa] - dx : X[sa], ay = ma ? Y[sa] - dy : Y[sa], az = ma ? Z[sa] - dz : Z[sa];
+      const T bx = mb ? X[sb] - dx : X[sb], by = mb ? Y[sb] - dy : Y[sb], bz = mb ? Z[sb] - dz : Z[sb];
+      const double ex = (double)ax - (double)bx, ey = (double)ay - (double)by, ez = (double)az - (double)bz;
+      const double r = sqrt(ex * ex + ey * ey + ez * ez);
+      const double d = r - a.p.target_bond_length;
+      e += a.p.bond_epsilon * (d * d);
+      far = fmax(far, r);
+    }
+    longest = warp_max(far);
+    return warp_sum(e);
+  };
+  auto write_trace = [&](int step, double longest) {
+    if (lane == 0) {
+      if (a.trace_f) {
+        double* t = a.trace_f + ((long long)c * a.num_steps + step) * 3;
+        t[0] = U; t[1] = Unb; t[2] = longest;
+      }
+      if (a.trace_i) a.trace_i[(long long)c * a.num_steps + step] = info;
+    }
+  };
+  // Draw the next move exactly as optimizer.py:214-244 does and publish the sweep.
+  auto propose = [&]() {
+    kb = (int)pcg_bounded(rng, (uint32_t)B);                       // :214
+    const int sa = bslot[2 * kb], sb = bslot[2 * kb + 1];
+    const double bvx = (double)X[sb] - (double)X[sa];              // :215-217 (P[b1] - P[b0])
+    const double bvy = (double)Y[sb] - (double)Y[sa];
+    const double bvz = (double)Z[sb] - (double)Z[sa];
+    const int side = (int)pcg_bounded(rng, 2u);                    // :225
+    ms = bsu[2 * kb + side];
+    const double rnd = (pcg_double(rng) - 0.5) * 2.0;              // :229
+    // molecule centroid from the per-subunit sums                 // :236-237
+    double tx = 0.0, ty = 0.0, tz = 0.0;
+    for (int s = lane; s < S; s += 32) { tx += csum[3 * s]; ty += csum[3 * s + 1]; tz += csum[3 * s + 2]; }
+    tx = warp_sum(tx); ty = warp_sum(ty); tz = warp_sum(tz);
+    const double nms = (double)(suoff[ms + 1] - suoff[ms]);
+    const double cvx = csum[3 * ms] / nms - tx / N;
+    const double cvy = csum[3 * ms + 1] / nms - ty / N;
+    const double cvz = csum[3 * ms + 2] / nms - tz / N;
+    kind = (int)pcg_bounded(rng, 2u);                              // :242-244
+    const double ss = a.p.step_size;
+    double vx, vy, vz;
+    if (kind == 0) { vx = ((-bvx) * ss) * rnd; vy = ((-bvy) * ss) * rnd; vz = ((-bvz) * ss) * rnd; }   // :233
+    else           { vx = (cvx * ss) * rnd;    vy = (cvy * ss) * rnd;    vz = (cvz * ss) * rnd; }      // :238
+    tvx = (T)vx; tvy = (T)vy; tvz = (T)vz;
+    const int n = fill_rows(ms, tvx, tvy, tvz);                    // :248-252  (pos - vector)
+    double longest;
+    Ub_trial = bond_terms(ms, tvx, tvy, tvz, longest);
+    if (lane == 0) {
+      ctl->nrows = n; ctl->c0 = 0; ctl->g0 = suoff[ms]; ctl->g1 = suoff[ms + 1]; ctl->c1 = N; ctl->ms = ms;
+    }
+  };
+
+  // ---------------------------------------------------------------- step 0: full evaluation
+  // For every subunit s: cross terms against all later subunits (each cross pair once)
+  // and the strict lower triangle inside s.
+  for (int s = 0; s < S; ++s) {
+    if (warp == 0) {
+      const int n = fill_rows(s, (T)0, (T)0, (T)0);
+      if (lane == 0) { ctl->nrows = n; ctl->c0 = suoff[s + 1]; ctl->g0 = suoff[s + 1]; ctl->g1 = suoff[s + 1]; ctl->c1 = N; ctl->ms = s; }
+    }
+    __syncthreads();
+    {
+      const int nrows = ctl->nrows;
+      Cols cross{ctl->c0, ctl->g0, ctl->g1, ctl->c1};
+      double part = pair_sweep<T, MUK, false>(Q, nrows, X, Y, Z, colsum, cross, term);
+      part = warp_sum(part);
+      const int r0 = suoff[s];
+      Cols own{r0, r0 + nrows, r0 + nrows, r0 + nrows};
+      double tri = pair_sweep<T, MUK, true>(Q, nrows, X, Y, Z, (T*)nullptr, own, term);
+      tri = warp_sum(tri);
+      if (lane == 0) { wsum[warp] = part; wsum[32 + warp] = tri; }
+    }
+    __syncthreads();
+    if (warp == 0) {
+      for (int w = 0; w < nwarps; ++w) e_intra += wsum[32 + w];
+      for (int t = s + 1; t < S; ++t) {
+        double v = 0.0;
+        for (int j = suoff[t] + lane; j < suoff[t + 1]; j += 32) v += (double)colsum[j];
+        v = warp_sum(v) * scale;
+        if (lane == 0) { E[s * S + t] = v; E[t * S + s] = v; }
+      }
+      const unsigned long long n = (unsigned long long)ctl->nrows;
+      pair_count += n * (unsigned long long)(N - suoff[s + 1]) + n * (n - 1ULL) / 2ULL;
+    }
+  }
+  if (warp == 0) {
+    __syncwarp();
+    e_intra *= scale;
+    double cross = 0.0;
+    for (int k = lane; k < S * S; k += 32) { const int s = k / S, t = k - s * S; if (t > s) cross += E[k]; }
+    Unb = warp_sum(cross) + e_intra;
+    for (int s = 0; s < S; ++s) refresh_csum(s);
+    double longest;
+    U = Unb + bond_terms(-1, (T)0, (T)0, (T)0, longest);
+    info = -1;
+    write_trace(0, longest);
+    if (a.num_steps <= 1 && lane == 0) a.maxd[c] = longest;
+    __syncwarp();
+    if (a.num_steps > 1) propose();
+  }
+
+  // ---------------------------------------------------------------- Monte-Carlo steps
+  for (int step = 1; step < a.num_steps; ++step) {
+    __syncthreads();  // A: move published, positions of step-1 final
+    if (a.traj) {
+      const long long frame = ((long long)c * a.num_steps + (step - 1)) * N * 3;
+      for (int n = tid; n < N; n += nt) {
+        const long long dst = frame + 3LL * a.perm[n];
+        store_io<Tio>(a.traj, dst + 0, (double)X[n] + origin[0]);
+        store_io<Tio>(a.traj, dst + 1, (double)Y[n] + origin[1]);
+        store_io<Tio>(a.traj, dst + 2, (double)Z[n] + origin[2]);
+      }
+    }
+    {
+      Cols others{ctl->c0, ctl->g0, ctl->g1, ctl->c1};
+      double part = pair_sweep<T, MUK, false>(Q, ctl->nrows, X, Y, Z, colsum, others, term);
+      part = warp_sum(part);
+      if (lane == 0) wsum[warp] = part;
+    }
+    __syncthreads();  // B: column sums and warp totals published
+    if (warp == 0) {
+      double fresh = 0.0;
+      for (int w = 0; w < nwarps; ++w) fresh += wsum[w];
+      fresh *= scale;
+      double old = 0.0;
+      for (int t = lane; t < S; t += 32) old += (t == ms) ? 0.0 : E[ms * S + t];
+      old = warp_sum(old);
+      const double Unb_new = Unb + (fresh - old);
+      const double U_new = Unb_new + Ub_trial;
+      bool ok;
+      if (U_new < U) ok = true;                                           // mc_operations.py:46-47
+      else ok = exp(-a.p.beta * (U_new - U)) > pcg_double(rng);           // mc_operations.py:49-52
+      const int r0 = suoff[ms], n = suoff[ms + 1] - r0;
+      pair_count += (unsigned long long)n * (unsigned long long)(N - n);
+      if (ok) {
+        for (int i = lane; i < n; i += 32) { const Row4<T> q = Q[i]; X[r0 + i] = q.x; Y[r0 + i] = q.y; Z[r0 + i] = q.z; }
+        for (int t = 0; t < S; ++t) {
+          if (t == ms) continue;
+          double v = 0.0;
+          for (int j = suoff[t] + lane; j < suoff[t + 1]; j += 32) v += (double)colsum[j];
+          v = warp_sum(v) * scale;
+          if (lane == 0) { E[ms * S + t] = v; E[t * S + ms] = v; }
+        }
+        U = U_new; Unb = Unb_new; ++n_acc;
+        __syncwarp();
+        refresh_csum(ms);
+      } else if (a.inexact_undo) {
+        // reference optimizer.py:273-277: translate the moved atoms by -tv again
+        for (int i = lane; i < n; i += 32) {
+          const Row4<T> q = Q[i];
+          X[r0 + i] = q.x - (-tvx); Y[r0 + i] = q.y - (-tvy); Z[r0 + i] = q.z - (-tvz);
+        }
+        __syncwarp();
+        refresh_csum(ms);
+      }
+      __syncwarp();
+      info = kb | ((ok ? 1 : 0) << 16) | (kind << 17) | (ms << 18);
+      const bool last = (step + 1 == a.num_steps);
+      if (a.trace_f || last) {
+        double longest;
+        (void)bond_terms(-1, (T)0, (T)0, (T)0, longest);
+        write_trace(step, longest);
+        if (last && lane == 0) a.maxd[c] = longest;
+      } else {
+        write_trace(step, 0.0);
+      }
+      if (!last) propose();
+    }
+  }
+  __syncthreads();
+
+  // ---------------------------------------------------------------- epilogue
+  for (int n = tid; n < N; n += nt) {
+    const long long at = 3LL * a.perm[n];
+    const double px = (double)X[n] + origin[0], py = (double)Y[n] + origin[1], pz = (double)Z[n] + origin[2];
+    const long long dst = (long long)c * N * 3 + at;
+    store_io<Tio>(a.pos_out, dst + 0, px); store_io<Tio>(a.pos_out, dst + 1, py); store_io<Tio>(a.pos_out, dst + 2, pz);
+    if (a.traj) {
+      const long long fr = ((long long)c * a.num_steps + (a.num_steps > 0 ? a.num_steps - 1 : 0)) * N * 3 + at;
+      store_io<Tio>(a.traj, fr + 0, px); store_io<Tio>(a.traj, fr + 1, py); store_io<Tio>(a.traj, fr + 2, pz);
+    }
+  }
+  if (warp == 0 && lane == 0) {
+    a.U[c] = U; a.Unb[c] = Unb; a.n_accept[c] = n_acc; a.last_info[c] = info;
+    if (a.pairs) a.pairs[c] = pair_count;
+    pcg_store(rng, a.rng + 6LL * c);
+  }
+}
+
+#endif  // __CUDACC__
+
+}  // namespace mch

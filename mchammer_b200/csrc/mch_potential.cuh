@@ -1,0 +1,127 @@
+// mch_potential.cuh -- standalone potential of a batch of molecules (no subunit knowledge).
+//
+// Replaces Optimizer.compute_potential / _compute_nonbonded_potential
+// (reference optimizer.py:114-142): U_nb = sum over ALL atom pairs of eps (sigma/r)^mu,
+// U = U_nb + sum_b eps_b (r_b - R_t)^2, plus the longest listed bond
+// (optimizer.py:174-183).  One CTA per molecule; atoms staged once into shared memory;
+// the N(N-1)/2 pairs are covered by row blocks of ROWB atoms swept against all later
+// atoms (cross part) and against themselves (strict lower triangle), both through
+// pair_sweep.  The long-bond harmonic term is fused into the same launch.
+#pragma once
+
+#include "mch_device.cuh"
+#include "mch_optimize.cuh"  // align_up, load_io
+
+namespace mch {
+
+struct PotArgs {
+  const void* pos;  // [C][N][3] io dtype
+  int C, N, B;
+  const int* bonds;  // [B][2] atom ids
+  Params p;
+  int mu_int;
+  double* U;     // [C]
+  double* Unb;   // [C]
+  double* maxd;  // [C] (0 when B == 0)
+};
+
+constexpr int POT_ROWB = 64;
+
+struct PotLayout { int x, y, z, rows, wsum, total; };
+
+MCH_HD PotLayout pot_layout(int N, int tsize) {
+  PotLayout L;
+  const int np = align_up(N, 8);
+  int o = 0;
+  L.x = o; o += np * tsize;
+  L.y = o; o += np * tsize;
+  L.z = o; o += np * tsize;
+  o = align_up(o, 32);
+  L.rows = o; o += POT_ROWB * 4 * tsize;
+  L.wsum = o; o += 3 * 32 * 8;
+  L.total = align_up(o, 16);
+  return L;
+}
+
+#ifdef __CUDACC__
+
+template <typename T, typename Tio, int MUK>
+__global__ void __launch_bounds__(256)
+mch_potential_kernel(const __grid_constant__ PotArgs a) {
+  extern __shared__ __align__(32) unsigned char smem[];
+  const int c = blockIdx.x;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int nt = blockDim.x, nwarps = nt >> 5;
+  const int N = a.N;
+  const PotLayout L = pot_layout(N, (int)sizeof(T));
+  T* X = reinterpret_cast<T*>(smem + L.x);
+  T* Y = reinterpret_cast<T*>(smem + L.y);
+  T* Z = reinterpret_cast<T*>(smem + L.z);
+  Row4<T>* Q = reinterpret_cast<Row4<T>*>(smem + L.rows);
+  double* wsum = reinterpret_cast<double*>(smem + L.wsum);
+
+  const PairTerm<T, MUK> term(a.p.nonbond_mu, a.mu_int);
+  const double scale = a.p.nonbond_epsilon * pow(a.p.nonbond_sigma, a.p.nonbond_mu);
+  const long long base = (long long)c * N * 3;
+
+  double origin[3] = {0.0, 0.0, 0.0};
+  if (sizeof(T) == 4) {  // centred frame for fp32 (pair distances are translation invariant)
+    double sx = 0.0, sy = 0.0, sz = 0.0;
+    for (int n = tid; n < N; n += nt) {
+      sx += load_io<Tio>(a.pos, base + 3LL * n + 0);
+      sy += load_io<Tio>(a.pos, base + 3LL * n + 1);
+      sz += load_io<Tio>(a.pos, base + 3LL * n + 2);
+    }
+    sx = warp_sum(sx); sy = warp_sum(sy); sz = warp_sum(sz);
+    if (lane == 0) { wsum[warp] = sx; wsum[32 + warp] = sy; wsum[64 + warp] = sz; }
+    __syncthreads();
+    for (int w = 0; w < nwarps; ++w) { origin[0] += wsum[w]; origin[1] += wsum[32 + w]; origin[2] += wsum[64 + w]; }
+    origin[0] /= N; origin[1] /= N; origin[2] /= N;
+    __syncthreads();
+  }
+  for (int n = tid; n < N; n += nt) {
+    X[n] = (T)(load_io<Tio>(a.pos, base + 3LL * n + 0) - origin[0]);
+    Y[n] = (T)(load_io<Tio>(a.pos, base + 3LL * n + 1) - origin[1]);
+    Z[n] = (T)(load_io<Tio>(a.pos, base + 3LL * n + 2) - origin[2]);
+  }
+  __syncthreads();
+
+  double mine = 0.0;
+  for (int r0 = 0; r0 < N; r0 += POT_ROWB) {
+    const int nrows = (N - r0) < POT_ROWB ? (N - r0) : POT_ROWB;
+    for (int i = tid; i < nrows; i += nt) {
+      Row4<T> q; q.x = X[r0 + i]; q.y = Y[r0 + i]; q.z = Z[r0 + i]; q.w = (T)0;
+      Q[i] = q;
+    }
+    __syncthreads();
+    const int r1 = r0 + nrows;
+    Cols later{r1, r1, r1, N};
+    mine += pair_sweep<T, MUK, false>(Q, nrows, X, Y, Z, (T*)nullptr, later, term);
+    Cols own{r0, r1, r1, r1};
+    mine += pair_sweep<T, MUK, true>(Q, nrows, X, Y, Z, (T*)nullptr, own, term);
+    __syncthreads();
+  }
+  mine = warp_sum(mine);
+  if (lane == 0) wsum[warp] = mine;
+  __syncthreads();
+  if (warp == 0) {
+    double unb = 0.0;
+    for (int w = 0; w < nwarps; ++w) unb += wsum[w];
+    unb *= scale;
+    double e = 0.0, far = 0.0;
+    for (int b = lane; b < a.B; b += 32) {
+      const int sa = a.bonds[2 * b], sb = a.bonds[2 * b + 1];
+      const double ex = (double)X[sa] - (double)X[sb], ey = (double)Y[sa] - (double)Y[sb], ez = (double)Z[sa] - (double)Z[sb];
+      const double r = sqrt(ex * ex + ey * ey + ez * ez);
+      const double d = r - a.p.target_bond_length;
+      e += a.p.bond_epsilon * (d * d);
+      far = fmax(far, r);
+    }
+    e = warp_sum(e); far = warp_max(far);
+    if (lane == 0) { a.Unb[c] = unb; a.U[c] = unb + e; a.maxd[c] = far; }
+  }
+}
+
+#endif  // __CUDACC__
+
+}  // namespace mch

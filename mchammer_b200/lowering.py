@@ -1,0 +1,123 @@
+"""Lowering: ``Molecule`` + ``bond_pair_ids`` + ``subunits``  ->  flat arrays for the kernels.
+
+The kernels want every subunit to be a contiguous *slot* range, so atoms are permuted
+(``perm[slot] = atom id``); positions stay in the caller's atom order in HBM and are
+gathered through ``perm`` once per chain.  Semantics preserved from the reference:
+
+* subunit order == dict order of ``subunits``; a bond end belongs to the FIRST subunit that
+  contains it (reference optimizer.py:220-221); an end in no subunit raises StopIteration,
+  which is what the reference's bare ``next(...)`` does;
+* the order inside a bond pair is the caller's (sign of the bond vector, utilities.py:24-31);
+* atoms that are in no subunit never move but still count in potentials and centroids:
+  they become one trailing static group;
+* Collapser: hydrogens are skipped by the contact test (collapser.py:77) -> within each
+  subunit the non-H atoms are put first and counted in ``n_heavy``.
+"""
+
+from __future__ import annotations
+
+from dataclasses import dataclass
+from typing import Iterable, Mapping, Sequence
+
+import numpy as np
+
+
+@dataclass
+class LoweredTopology:
+    n_atoms: int
+    n_subunits: int          # including the trailing static group, if any
+    n_user_subunits: int     # entries of the caller's dict
+    perm: np.ndarray         # int32 [N]   slot -> atom id
+    su_offsets: np.ndarray   # int32 [S+1]
+    bonds: np.ndarray        # int32 [B,2] atom ids, caller's order
+    bond_su: np.ndarray      # int32 [B,2] subunit index of each end (-1 where unknown)
+    n_heavy: np.ndarray      # int32 [S]   non-H atoms per subunit (== size if no elements)
+    max_subunit_atoms: int
+    subunit_keys: list       # caller's keys, dict order
+    subunit_sizes: list[int]
+
+    @property
+    def n_bonds(self) -> int:
+        return int(self.bonds.shape[0])
+
+
+def _as_pairs(bond_pair_ids: Iterable[Sequence[int]]) -> np.ndarray:
+    pairs = [(int(b[0]), int(b[1])) for b in bond_pair_ids]
+    return np.array(pairs, dtype=np.int32).reshape(-1, 2)
+
+
+def lower_topology(
+    n_atoms: int,
+    bond_pair_ids: Iterable[Sequence[int]],
+    subunits: Mapping,
+    elements: Sequence[str] | None = None,
+    require_bond_subunits: bool = True,
+) -> LoweredTopology:
+    """Build the slot permutation and the bond/subunit tables (host, O(N + B*S))."""
+    bonds = _as_pairs(bond_pair_ids)
+    if bonds.size and (bonds.min() < 0 or bonds.max() >= n_atoms):
+        raise ValueError("bond_pair_ids refers to an atom id outside the molecule")
+
+    keys = list(subunits)
+    owner = np.full(n_atoms, -1, dtype=np.int64)
+    members: list[list[int]] = []
+    for index, key in enumerate(keys):
+        ids = [int(a) for a in subunits[key]]
+        if len(ids) == 0:
+            raise ValueError(f"subunit {key!r} has no atoms")
+        for atom in ids:
+            if atom < 0 or atom >= n_atoms:
+                raise ValueError(f"subunit {key!r} refers to atom {atom} outside the molecule")
+            if owner[atom] == index:
+                raise ValueError(f"atom {atom} is listed twice in subunit {key!r}")
+            if owner[atom] != -1:
+                raise ValueError(
+                    f"atom {atom} is in two subunits ({keys[owner[atom]]!r} and {key!r}); "
+                    "overlapping subunits cannot be moved rigidly on the device"
+                )
+            owner[atom] = index
+        members.append(ids)
+    loose = [int(a) for a in np.nonzero(owner < 0)[0]]
+    if loose:
+        members.append(loose)  # static group: never selected, still interacts
+
+    is_h = None
+    if elements is not None:
+        is_h = np.array([e == "H" for e in elements], dtype=bool)
+        members = [
+            [a for a in ids if not is_h[a]] + [a for a in ids if is_h[a]] for ids in members
+        ]
+
+    perm = np.array([a for ids in members for a in ids], dtype=np.int32)
+    sizes = [len(ids) for ids in members]
+    su_offsets = np.concatenate([[0], np.cumsum(sizes)]).astype(np.int32)
+    if is_h is None:
+        n_heavy = np.array(sizes, dtype=np.int32)
+    else:
+        n_heavy = np.array([int(sum(1 for a in ids if not is_h[a])) for ids in members], dtype=np.int32)
+
+    bond_su = np.full((bonds.shape[0], 2), -1, dtype=np.int32)
+    n_user = len(keys)
+    for b, (a1, a2) in enumerate(bonds):
+        for side, atom in enumerate((a1, a2)):
+            index = int(owner[atom])
+            if index < 0 or index >= n_user:
+                if require_bond_subunits:
+                    # reference: next(i for i in subunits if atom in subunits[i]) -> StopIteration
+                    raise StopIteration(f"atom {int(atom)} of bond {(int(a1), int(a2))} is in no subunit")
+                continue
+            bond_su[b, side] = index
+
+    return LoweredTopology(
+        n_atoms=n_atoms,
+        n_subunits=len(members),
+        n_user_subunits=n_user,
+        perm=perm,
+        su_offsets=su_offsets,
+        bonds=bonds,
+        bond_su=bond_su,
+        n_heavy=n_heavy,
+        max_subunit_atoms=max(sizes) if sizes else 0,
+        subunit_keys=keys,
+        subunit_sizes=[len(subunits[k]) for k in keys],
+    )

@@ -1,0 +1,353 @@
+"""``Optimizer``: the reference's Metropolis driver, running on a B200.
+
+Same constructor and methods as reference src/mchammer/_internal/optimizer.py:19-438
+(``get_result``, ``get_trajectory``, ``compute_potential`` and the private helpers its
+tests call), plus :meth:`Optimizer.get_results_batch` for many independent chains.
+All arithmetic of the step loop happens in ``mch_optimize_batch`` (CUDA); this class
+lowers the inputs, launches, and raises the device records into the reference's
+``Molecule`` / ``MCStepResult`` / ``Result`` objects and log text.
+"""
+
+from __future__ import annotations
+
+import time
+from dataclasses import dataclass
+from typing import Iterable, Sequence
+
+import numpy as np
+
+from . import engine, native, rngstate
+from .lowering import LoweredTopology, lower_topology
+from .records import MCStepResult, Result
+from .structure import Molecule
+
+
+@dataclass
+class BatchResult:
+    """Outcome of ``C`` independent chains (host arrays)."""
+
+    positions: np.ndarray            # [C,N,3]
+    system_potential: np.ndarray     # [C]
+    nonbonded_potential: np.ndarray  # [C]
+    max_bond_distance: np.ndarray    # [C]
+    n_accepted: np.ndarray           # [C] accepted moves
+    last_passed: np.ndarray          # [C] 1/0; -1 when no move was made
+    last_bond_index: np.ndarray      # [C] index into bond_pair_ids; -1 when no move
+    pair_evals: np.ndarray           # [C] pair terms the kernel evaluated
+    num_steps: int
+    seconds: float                   # wall time of the call (H2D + kernel + D2H)
+
+    def __len__(self) -> int:
+        return int(self.positions.shape[0])
+
+    def molecule(self, index: int, template: Molecule) -> Molecule:
+        return template.with_position_matrix(np.array(self.positions[index], dtype=np.float64))
+
+
+def _unpack_info(info: np.ndarray):
+    info = np.asarray(info, dtype=np.int64)
+    none = info < 0
+    bond = np.where(none, -1, info & 0xFFFF)
+    passed = np.where(none, -1, (info >> 16) & 1)
+    kind = np.where(none, -1, (info >> 17) & 1)
+    moved = np.where(none, -1, (info >> 18) & 0x1FFF)
+    return bond, passed, kind, moved
+
+
+class Optimizer:
+    """Optimize target bonds with a Metropolis MC of rigid subunit translations (on CUDA)."""
+
+    def __init__(  # noqa: PLR0913
+        self,
+        step_size: float,
+        target_bond_length: float,
+        num_steps: int,
+        bond_epsilon: float = 50,
+        nonbond_epsilon: float = 20,
+        nonbond_sigma: float = 1.2,
+        nonbond_mu: float = 3,
+        beta: float = 2,
+        random_seed: int | None = 1000,
+        *,
+        precision: str = "fp64",
+        device: int | None = None,
+    ) -> None:
+        """Reference arguments (optimizer.py:27-38) plus two keyword-only device options.
+
+        precision:
+            ``"fp64"`` reproduces the reference's accept/reject sequence (pair terms,
+            sums and positions in float64); ``"fp32"`` evaluates pair terms and stores
+            positions in float32 (potentials within 1e-4 relative of fp64).
+        device:
+            CUDA device index (default: the current device).
+        """
+        self._step_size = step_size
+        self._target_bond_length = target_bond_length
+        self._num_steps = num_steps
+        self._bond_epsilon = bond_epsilon
+        self._nonbond_epsilon = nonbond_epsilon
+        self._nonbond_sigma = nonbond_sigma
+        self._nonbond_mu = nonbond_mu
+        self._beta = beta
+        if precision not in engine.PRECISIONS:
+            raise ValueError(f"precision must be 'fp64' or 'fp32', got {precision!r}")
+        self._precision = precision
+        self._device = device
+        self._generator = (
+            np.random.default_rng() if random_seed is None else np.random.default_rng(random_seed)
+        )
+
+    # ------------------------------------------------------------------ scalar potentials
+    def _bond_potential(self, distance: float) -> float:
+        """eps_b (d - R_t)^2 -- reference optimizer.py:95-102 (scalar convenience form)."""
+        return self._bond_epsilon * (distance - self._target_bond_length) ** 2
+
+    def _nonbond_potential(self, distance: float) -> float:
+        """eps_nb (sigma / d)^mu -- reference optimizer.py:104-112 (scalar convenience form)."""
+        return self._nonbond_epsilon * ((self._nonbond_sigma / distance) ** self._nonbond_mu)
+
+    def _params(self) -> native.MchParams:
+        return engine.make_params(
+            self._step_size, self._target_bond_length, self._bond_epsilon,
+            self._nonbond_epsilon, self._nonbond_sigma, self._nonbond_mu, self._beta,
+        )
+
+    def _torch_device(self):
+        torch = native.require_cuda()
+        index = torch.cuda.current_device() if self._device is None else self._device
+        return torch.device("cuda", index)
+
+    # ------------------------------------------------------------------ potentials on device
+    def _potential(self, position_matrix: np.ndarray, bond_pair_ids) -> tuple[float, float, float]:
+        torch = native.require_cuda()
+        dev = self._torch_device()
+        pos = torch.from_numpy(np.ascontiguousarray(position_matrix, dtype=np.float64)).to(dev)
+        bonds = np.array([(int(b[0]), int(b[1])) for b in bond_pair_ids], dtype=np.int32).reshape(-1)
+        bonds_dev = torch.from_numpy(bonds).to(dev) if bonds.size else None
+        u, unb, far = engine.potential_on_device(
+            pos, bonds_dev, bonds.size // 2, self._params(), self._precision
+        )
+        return float(u.item()), float(unb.item()), float(far.item())
+
+    def _compute_nonbonded_potential(self, position_matrix: np.ndarray) -> float:
+        """Sum of eps (sigma/r)^mu over all atom pairs (reference optimizer.py:114-120)."""
+        return self._potential(position_matrix, ())[1]
+
+    def compute_potential(self, mol: Molecule, bond_pair_ids) -> tuple[float, float]:
+        """``(system_potential, nonbonded_potential)`` of ``mol`` (reference optimizer.py:122-142)."""
+        u, unb, _ = self._potential(mol.get_position_matrix(), bond_pair_ids)
+        return u, unb
+
+    # ------------------------------------------------------------------ log text
+    def _output_top_lines(self) -> str:
+        rule = "=" * 52 + "\n"
+
+        def banner(text: str) -> str:  # 52 columns, odd padding goes to the left
+            left = (52 - len(text) + 1) // 2
+            return (" " * left + text).ljust(52) + "\n"
+
+        head = "".join(
+            banner(t) for t in ("MCHammer optimisation", "-" * 21, "Andrew Tarzia", "-" * 21, "")
+        )
+        settings = (
+            f"{'Settings:':<52}\n"
+            f" step size = {self._step_size} \n"
+            f" target bond length = {self._target_bond_length} \n"
+            f" num. steps = {self._num_steps} \n"
+            f" bond epsilon = {self._bond_epsilon} \n"
+            f" nonbond epsilon = {self._nonbond_epsilon} \n"
+            f" nonbond sigma = {self._nonbond_sigma} \n"
+            f" nonbond mu = {self._nonbond_mu} \n"
+            f" beta = {self._beta} \n"
+        )
+        return rule + head + settings + rule + "\n"
+
+    # ------------------------------------------------------------------ one molecule
+    def _run_single(self, mol: Molecule, bond_pair_ids, subunits, want_trace: bool):
+        torch = native.require_cuda()
+        dev = self._torch_device()
+        topo = lower_topology(
+            mol.get_num_atoms(), bond_pair_ids, subunits,
+            require_bond_subunits=self._num_steps > 1,
+        )
+        dtopo = engine.upload_topology(topo, dev.index)
+        pos = torch.from_numpy(mol.get_position_matrix()).to(dev)
+        words = rngstate.words_from_bit_generator(self._generator.bit_generator)
+        rng_dev = engine.rng_words_to_device(words[None, :], dev)
+        out = engine.optimize_on_device(
+            dtopo, pos, 1, rng_dev, self._params(), self._num_steps, self._precision,
+            want_trace=want_trace, want_trajectory=want_trace,
+        )
+        # the generator of this Optimizer advances across calls, like the reference's
+        rngstate.words_to_bit_generator(
+            engine.rng_words_from_device(out.rng_state)[0], self._generator.bit_generator
+        )
+        return topo, out
+
+    @staticmethod
+    def _step_log(step, u, unb, far, bond_row, passed) -> str:
+        if passed is None:
+            return f"{step} {u} {unb} {far} -- --\n"
+        return f"{step} {u} {unb} {far} {bond_row} {'T' if passed else 'F'}\n"
+
+    def get_result(self, mol: Molecule, bond_pair_ids, subunits: dict) -> tuple[Molecule, MCStepResult]:
+        """Final molecule and the record of the last step (reference optimizer.py:392-438)."""
+        topo, out = self._run_single(mol, bond_pair_ids, subunits, want_trace=False)
+        positions = out.positions[0].cpu().numpy().astype(np.float64)
+        u = float(out.system_potential.item())
+        unb = float(out.nonbonded_potential.item())
+        far = float(out.max_bond_distance.item())
+        bond, passed, _, _ = _unpack_info(out.last_step_info.cpu().numpy())
+        last_step = max(int(self._num_steps), 1) - 1
+        if passed[0] < 0:
+            flag, row = None, None
+        else:
+            flag, row = bool(passed[0]), np.asarray(bond_pair_ids)[int(bond[0])]
+        record = MCStepResult(
+            step=last_step, position_matrix=positions, passed=flag, system_potential=u,
+            nonbonded_potential=unb, max_bond_distance=far,
+            log=self._step_log(last_step, u, unb, far, row, flag),
+        )
+        return mol.with_position_matrix(positions), record
+
+    def get_trajectory(self, mol: Molecule, bond_pair_ids, subunits: dict) -> tuple[Molecule, Result]:
+        """Final molecule and every step's record + log (reference optimizer.py:308-390)."""
+        result = Result(start_time=time.time())
+        result.update_log(self._output_top_lines())
+        result.update_log(f"There are {len(bond_pair_ids)} bonds to optimize.\n")
+        result.update_log(
+            f"There are {len(subunits)} sub units with N atoms:\n"
+            f"{[len(subunits[i]) for i in subunits]}\n"
+        )
+        rule = "=" * 52 + "\n"
+        result.update_log(rule + " " * 17 + "Running optimisation!" + " " * 14 + "\n" + rule + "\n")
+        result.update_log("step system_potential nonbond_potential max_dist opt_bbs updated?\n")
+
+        topo, out = self._run_single(mol, bond_pair_ids, subunits, want_trace=True)
+        trace = out.trace_potentials[0].cpu().numpy()
+        bond, passed, _, _ = _unpack_info(out.trace_info[0].cpu().numpy())
+        frames = out.trajectory[0].cpu().numpy().astype(np.float64)
+        bond_table = np.asarray(bond_pair_ids)
+        for step in range(trace.shape[0]):
+            u, unb, far = (float(x) for x in trace[step])
+            if passed[step] < 0:
+                flag, row = None, None
+            else:
+                flag, row = bool(passed[step]), bond_table[int(bond[step])]
+            result.add_step_result(
+                MCStepResult(
+                    step=step, position_matrix=frames[step], passed=flag, system_potential=u,
+                    nonbonded_potential=unb, max_bond_distance=far,
+                    log=self._step_log(step, u, unb, far, row, flag),
+                )
+            )
+        num_passed = result.get_number_passed()
+        result.update_log(
+            "\n============================================\n"
+            "Optimisation done:\n"
+            f"{num_passed} steps passed: {(num_passed / self._num_steps) * 100}%\n"
+            f"Total optimisation time: {round(result.get_timing(time.time()), 4)}s\n"
+            "============================================\n"
+        )
+        final = out.positions[0].cpu().numpy().astype(np.float64)
+        return mol.with_position_matrix(final), result
+
+    # ------------------------------------------------------------------ many chains
+    def get_results_batch(
+        self,
+        mol: Molecule,
+        bond_pair_ids,
+        subunits: dict,
+        seeds: Sequence[int] | None = None,
+        n_chains: int | None = None,
+        positions: np.ndarray | None = None,
+        devices: Sequence[int] | None = None,
+        io_dtype=np.float64,
+        threads_per_chain: int = 0,
+    ) -> BatchResult:
+        """Run many independent chains of the same topology (NEW; no reference counterpart).
+
+        Chain ``c`` is what ``Optimizer(..., random_seed=seeds[c]).get_result(...)`` would
+        do to molecule ``c``: ``positions[c]`` if ``positions`` ([C,N,3]) is given, else
+        ``mol`` itself for every chain.  ``seeds`` defaults to ``random_seed + c`` drawn from
+        this optimizer's generator.  Chains are split contiguously over ``devices`` (default:
+        this optimizer's device); there is no inter-device communication -- results are
+        concatenated on the host.
+        """
+        torch = native.require_cuda()
+        start = time.perf_counter()
+        if positions is not None:
+            positions = np.ascontiguousarray(positions, dtype=io_dtype)
+            if positions.ndim != 3 or positions.shape[1:] != (mol.get_num_atoms(), 3):
+                raise ValueError("positions must have shape [C, n_atoms, 3]")
+            if n_chains is None:
+                n_chains = positions.shape[0]
+        if seeds is not None:
+            seeds = [int(s) for s in seeds]
+            if n_chains is None:
+                n_chains = len(seeds)
+        if n_chains is None:
+            raise ValueError("give seeds, positions or n_chains")
+        if seeds is None:
+            base = int(self._generator.integers(0, 2**63))
+            seeds = [base + c for c in range(n_chains)]
+        if len(seeds) != n_chains or (positions is not None and positions.shape[0] != n_chains):
+            raise ValueError("seeds / positions / n_chains disagree on the number of chains")
+
+        topo = lower_topology(
+            mol.get_num_atoms(), bond_pair_ids, subunits,
+            require_bond_subunits=self._num_steps > 1,
+        )
+        words = rngstate.seed_states(seeds)
+        if devices is None:
+            devices = [self._torch_device().index]
+        shards = shard_bounds(n_chains, len(devices))
+        base_pos = np.ascontiguousarray(mol.get_position_matrix(), dtype=io_dtype)
+
+        pending = []
+        for dev_index, (lo, hi) in zip(devices, shards):
+            if hi == lo:
+                continue
+            with torch.cuda.device(dev_index):
+                dev = torch.device("cuda", dev_index)
+                dtopo = engine.upload_topology(topo, dev_index)
+                if positions is None:
+                    pos_dev = engine.host_to_device(base_pos[None], dev, pin=False)
+                else:
+                    pos_dev = engine.host_to_device(positions[lo:hi], dev)
+                rng_dev = engine.rng_words_to_device(words[lo:hi], dev)
+                out = engine.optimize_on_device(
+                    dtopo, pos_dev, hi - lo, rng_dev, self._params(), self._num_steps,
+                    self._precision, threads_per_chain=threads_per_chain,
+                )
+                pending.append((lo, hi, out))
+
+        n = mol.get_num_atoms()
+        res = BatchResult(
+            positions=np.empty((n_chains, n, 3), dtype=io_dtype),
+            system_potential=np.empty(n_chains), nonbonded_potential=np.empty(n_chains),
+            max_bond_distance=np.empty(n_chains), n_accepted=np.empty(n_chains, dtype=np.int64),
+            last_passed=np.empty(n_chains, dtype=np.int64),
+            last_bond_index=np.empty(n_chains, dtype=np.int64),
+            pair_evals=np.empty(n_chains, dtype=np.int64),
+            num_steps=max(int(self._num_steps), 1), seconds=0.0,
+        )
+        for lo, hi, out in pending:  # .cpu() synchronises with each device in turn
+            res.positions[lo:hi] = out.positions.cpu().numpy()
+            res.system_potential[lo:hi] = out.system_potential.cpu().numpy()
+            res.nonbonded_potential[lo:hi] = out.nonbonded_potential.cpu().numpy()
+            res.max_bond_distance[lo:hi] = out.max_bond_distance.cpu().numpy()
+            res.n_accepted[lo:hi] = out.n_accepted.cpu().numpy()
+            bond, passed, _, _ = _unpack_info(out.last_step_info.cpu().numpy())
+            res.last_passed[lo:hi] = passed
+            res.last_bond_index[lo:hi] = bond
+            res.pair_evals[lo:hi] = out.pair_evals.cpu().numpy()
+        res.seconds = time.perf_counter() - start
+        return res
+
+
+def shard_bounds(n_items: int, n_shards: int) -> list[tuple[int, int]]:
+    """Contiguous, balanced ``[lo, hi)`` ranges: shard ``g`` gets items ``g*n/G .. (g+1)*n/G``."""
+    if n_shards <= 0:
+        raise ValueError("n_shards must be positive")
+    return [((g * n_items) // n_shards, ((g + 1) * n_items) // n_shards) for g in range(n_shards)]

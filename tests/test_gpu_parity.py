@@ -1,0 +1,377 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against
+  (a) golden vectors produced by the unmodified reference (tests/golden/*.npz),
+  (b) the CPU oracle on the same seeded inputs,
+  (c) size-independent properties at BASELINE sizes.
+
+Tolerances (BASELINE.json north_star): fp64 mode reproduces the reference's accept/reject
+sequence exactly, potentials and positions within 1e-9 relative; fp32 mode keeps
+potentials within 1e-4 relative.
+"""
+
+from __future__ import annotations
+
+import numpy as np
+import pytest
+
+import mchammer_b200 as mch
+from mchammer_b200 import synthetic
+from oracle import mch_oracle as orc
+from tests.conftest import golden_bonds, golden_subunits, load_golden
+
+pytestmark = pytest.mark.gpu
+
+RTOL64 = 1e-9
+RTOL32 = 1e-4
+
+
+def golden_molecule(g) -> mch.Molecule:
+    return mch.Molecule(
+        atoms=tuple(mch.Atom(id=i, element_string=str(e)) for i, e in enumerate(g["elements"])),
+        bonds=tuple(mch.Bond(id=i, atom_ids=tuple(int(x) for x in b)) for i, b in enumerate(g["bonds"])),
+        position_matrix=g["pos0"],
+    )
+
+
+def _num(value):
+    """Golden scalars keep the Python type the reference was given (50 prints as '50', not '50.0')."""
+    value = np.asarray(value)
+    return int(value) if np.issubdtype(value.dtype, np.integer) else float(value)
+
+
+def golden_optimizer(g, **kw) -> mch.Optimizer:
+    return mch.Optimizer(
+        step_size=_num(g["step_size"]), target_bond_length=_num(g["target_bond_length"]),
+        num_steps=int(g["num_steps"]), bond_epsilon=_num(g["bond_epsilon"]),
+        nonbond_epsilon=_num(g["nonbond_epsilon"]), nonbond_sigma=_num(g["nonbond_sigma"]),
+        nonbond_mu=_num(g["nonbond_mu"]), beta=_num(g["beta"]), random_seed=int(g["seed"]), **kw,
+    )
+
+
+def rel_close(a, b, rtol):
+    a, b = np.asarray(a, float), np.asarray(b, float)
+    return np.all(np.abs(a - b) <= rtol * np.maximum(np.abs(b), 1e-300))
+
+
+# ------------------------------------------------------------------------- potentials
+def test_known_answer_potentials_fp64():
+    # reference tests/conftest.py:145-152, tests/optimizer/test_optimizer.py:37-62
+    opt = mch.Optimizer(step_size=0.1, target_bond_length=2.0, num_steps=100)
+    pos = np.array([[0, 1, 0], [1, 1, 0], [-1, 1, 0], [0, 10, 0], [1, 10, 0], [-1, 10, 0]])
+    assert np.isclose(opt._compute_nonbonded_potential(pos), 147.2965949864993, rtol=1e-13, atol=0)
+    mol = mch.Molecule(
+        atoms=[mch.Atom(i, "C") for i in range(6)],
+        bonds=[mch.Bond(0, (0, 1)), mch.Bond(1, (0, 2)), mch.Bond(2, (0, 3)), mch.Bond(3, (3, 4)), mch.Bond(4, (3, 5))],
+        position_matrix=pos,
+    )
+    u, unb = opt.compute_potential(mol, bond_pair_ids=((0, 3),))
+    assert np.isclose(unb, 147.2965949864993, rtol=1e-13, atol=0)
+    assert np.isclose(u, 2597.2965949864993, rtol=1e-13, atol=0)
+
+
+@pytest.mark.parametrize("precision,rtol", [("fp64", 1e-12), ("fp32", 1e-5)])
+def test_potentials_random_geometries(precision, rtol):
+    g = load_golden("potentials")
+    opt = mch.Optimizer(step_size=0.1, target_bond_length=2.0, num_steps=2, precision=precision)
+    for n in (2, 3, 17, 112, 300):
+        mol = mch.Molecule(atoms=[mch.Atom(i, "C") for i in range(n)], bonds=[], position_matrix=g[f"pos_{n}"])
+        u, unb = opt.compute_potential(mol, g[f"bonds_{n}"].tolist())
+        assert np.isclose(u, float(g[f"u_{n}"]), rtol=rtol, atol=0), (n, u, float(g[f"u_{n}"]))
+        assert np.isclose(unb, float(g[f"unb_{n}"]), rtol=rtol, atol=0)
+
+
+@pytest.mark.parametrize("mu", [2.0, 2.5, 3.0, 6.0, 12.0])
+@pytest.mark.parametrize("precision,rtol", [("fp64", 1e-11), ("fp32", 2e-5)])
+def test_potential_mu_variants_against_oracle(mu, precision, rtol):
+    rng = np.random.default_rng(5)
+    pos = rng.normal(scale=4.0, size=(150, 3))
+    bonds = [(0, 9), (3, 77), (140, 2)]
+    p = orc.OptimizerParams(0.25, 1.2, 2, nonbond_mu=mu, nonbond_sigma=1.4, nonbond_epsilon=7.0)
+    want_u, want_unb = orc.compute_potential(pos, bonds, p)
+    opt = mch.Optimizer(0.25, 1.2, 2, nonbond_mu=mu, nonbond_sigma=1.4, nonbond_epsilon=7.0, precision=precision)
+    mol = mch.Molecule(atoms=[mch.Atom(i, "C") for i in range(150)], bonds=[], position_matrix=pos)
+    u, unb = opt.compute_potential(mol, bonds)
+    assert np.isclose(unb, want_unb, rtol=rtol, atol=0)
+    assert np.isclose(u, want_u, rtol=rtol, atol=0)
+
+
+# ------------------------------------------------------------------------- MC traces vs reference
+TRACE_CASES = ["benzene_seed1000", "benzene_seed7", "benzene_mu2p5", "benzene_mu6", "toy_seed1000",
+               "poc_graph_seed1000", "poc_graph_seed7", "poc_graph_seed42", "poc_bb_seed1000"]
+
+
+@pytest.mark.parametrize("case", TRACE_CASES)
+def test_fp64_trajectory_matches_reference(case):
+    g = load_golden(case)
+    mol = golden_molecule(g)
+    opt = golden_optimizer(g)
+    out_mol, result = opt.get_trajectory(mol, golden_bonds(g), golden_subunits(g))
+    props = list(result.get_steps_properties())
+    assert len(props) == int(g["num_steps"])
+    assert result.get_step_count() == int(g["num_steps"]) - 1
+    passed = np.array([-1 if p["passed"] is None else int(p["passed"]) for _, p in props])
+    assert np.array_equal(passed, g["passed"]), "accept/reject sequence differs from the reference"
+    assert rel_close([p["system_potential"] for _, p in props], g["system_potential"], RTOL64)
+    assert rel_close([p["nonbonded_potential"] for _, p in props], g["nonbonded_potential"], RTOL64)
+    assert rel_close([p["max_bond_distance"] for _, p in props], g["max_bond_distance"], RTOL64)
+    assert np.allclose(out_mol.get_position_matrix(), g["final_positions"], rtol=RTOL64, atol=1e-9)
+    assert result.get_number_passed() == int(g["number_passed"])
+    if "positions" in g.files:
+        frames = np.array([f for _, f in result.get_trajectory()])
+        assert np.allclose(frames, g["positions"], rtol=RTOL64, atol=1e-9)
+    # log text: same lines as the reference (numbers compared numerically, words exactly)
+    got_lines = result.get_log().splitlines()
+    want_lines = str(g["log"]).splitlines()
+    assert len(got_lines) == len(want_lines)
+    for got, want in zip(got_lines, want_lines):
+        if want.startswith("Total optimisation time"):
+            assert got.startswith("Total optimisation time: ")
+            continue
+        gt, wt = got.split(), want.split()
+        if len(wt) >= 6 and wt[0].isdigit():
+            assert gt[0] == wt[0] and gt[4:] == wt[4:], (got, want)
+            assert rel_close([float(x) for x in gt[1:4]], [float(x) for x in wt[1:4]], RTOL64)
+        else:
+            assert got == want
+
+
+@pytest.mark.parametrize("case", ["benzene_seed1000", "poc_graph_seed1000", "poc_bb_seed1000"])
+def test_fp64_get_result_matches_reference(case):
+    g = load_golden(case)
+    mol = golden_molecule(g)
+    before = mol.get_position_matrix()
+    out_mol, last = golden_optimizer(g).get_result(mol, golden_bonds(g), golden_subunits(g))
+    assert np.array_equal(mol.get_position_matrix(), before), "input molecule was mutated"
+    assert last.step == int(g["num_steps"]) - 1
+    assert last.passed == bool(g["passed"][-1])
+    assert rel_close(last.system_potential, g["system_potential"][-1], RTOL64)
+    assert rel_close(last.nonbonded_potential, g["nonbonded_potential"][-1], RTOL64)
+    assert rel_close(last.max_bond_distance, g["max_bond_distance"][-1], RTOL64)
+    assert np.allclose(last.position_matrix, g["final_positions"], rtol=RTOL64, atol=1e-9)
+    assert np.allclose(out_mol.get_position_matrix(), g["final_positions"], rtol=RTOL64, atol=1e-9)
+
+
+def test_committed_example_molfiles():
+    # reference examples/poc_opt.mol etc. hold 4 decimals
+    ex = load_golden("reference_examples")
+    for case, name in (("benzene_seed1000", "benzene_opt"), ("poc_graph_seed1000", "poc_opt"),
+                       ("poc_bb_seed1000", "poc_opt_nci")):
+        g = load_golden(case)
+        out_mol, _ = golden_optimizer(g).get_result(golden_molecule(g), golden_bonds(g), golden_subunits(g))
+        assert np.abs(out_mol.get_position_matrix() - ex[name]).max() < 1.5e-4
+
+
+def test_generator_advances_across_calls():
+    g = load_golden("benzene_two_calls")
+    b = load_golden("benzene_seed1000")
+    mol = golden_molecule(b)
+    lb = golden_bonds(b)
+    su = mol.get_subunits(bond_pair_ids=lb)
+    opt = mch.Optimizer(step_size=0.25, target_bond_length=1.2, num_steps=40, random_seed=3)
+    m1, r1 = opt.get_result(mol, lb, su)
+    m2, r2 = opt.get_result(m1, lb, su)
+    assert np.allclose(m1.get_position_matrix(), g["first_positions"], rtol=RTOL64, atol=1e-9)
+    assert np.allclose(m2.get_position_matrix(), g["second_positions"], rtol=RTOL64, atol=1e-9)
+    assert rel_close(r1.system_potential, float(g["first_u"]), RTOL64)
+    assert rel_close(r2.system_potential, float(g["second_u"]), RTOL64)
+    assert int(bool(r1.passed)) == int(g["first_passed"]) and int(bool(r2.passed)) == int(g["second_passed"])
+
+
+def test_num_steps_one_and_zero():
+    g = load_golden("benzene_seed1000")
+    mol = golden_molecule(g)
+    for steps in (1, 0):
+        opt = mch.Optimizer(step_size=0.25, target_bond_length=1.2, num_steps=steps)
+        out_mol, last = opt.get_result(mol, golden_bonds(g), golden_subunits(g))
+        assert last.step == 0 and last.passed is None
+        assert last.log.endswith("-- --\n")
+        assert rel_close(last.system_potential, g["system_potential"][0], 1e-12)
+        assert np.array_equal(out_mol.get_position_matrix(), g["pos0"])
+
+
+# ------------------------------------------------------------------------- reference-style integration tests
+def test_reference_style_toy_run():
+    # mirrors reference tests/optimizer/test_optimizer.py:101-177
+    pos = np.array([[0, 1, 0], [1, 1, 0], [-1, 1, 0], [0, 10, 0], [1, 10, 0], [-1, 10, 0]])
+    bonds = [mch.Bond(0, (0, 1)), mch.Bond(1, (0, 2)), mch.Bond(2, (0, 3)), mch.Bond(3, (3, 4)), mch.Bond(4, (3, 5))]
+    molecule = mch.Molecule(atoms=[mch.Atom(i, "C") for i in range(6)], bonds=bonds, position_matrix=pos)
+    optimizer = mch.Optimizer(step_size=0.1, target_bond_length=2.0, num_steps=100)
+    subunits = molecule.get_subunits(bond_pair_ids=((0, 3),))
+    original = molecule.get_position_matrix()
+    mol, results = optimizer.get_trajectory(mol=molecule, bond_pair_ids=((0, 3),), subunits=subunits)
+    assert results.get_step_count() == 99
+    assert len(tuple(results.get_steps_properties())) == 100
+    final = results.get_final_position_matrix()
+    length = np.linalg.norm(mch.get_bond_vector(position_matrix=final, bond_pair=(0, 3)))
+    assert 1.5 < length < 2.5
+    for bond in molecule.get_bonds():
+        pair = (bond.get_atom1_id(), bond.get_atom2_id())
+        if pair != (0, 3):
+            assert np.isclose(mch.get_atom_distance(final, *pair), mch.get_atom_distance(original, *pair), atol=1e-6)
+
+
+# ------------------------------------------------------------------------- batched chains vs oracle
+@pytest.mark.parametrize("precision", ["fp64"])
+def test_batch_matches_oracle_on_synthetic_cage(precision):
+    mol, long_bonds, subunits = synthetic.cube_cage(atoms_per_subunit=10, seed=4, spread=6.0)
+    seeds = [1000 + c for c in range(6)]
+    steps = 80
+    opt = mch.Optimizer(step_size=0.25, target_bond_length=1.2, num_steps=steps, precision=precision)
+    got = opt.get_results_batch(mol, long_bonds, subunits, seeds=seeds)
+    p = orc.OptimizerParams(step_size=0.25, target_bond_length=1.2, num_steps=steps)
+    for c, seed in enumerate(seeds):
+        want = orc.optimizer_run(mol.get_position_matrix(), long_bonds, subunits, p, np.random.default_rng(seed))
+        assert int(got.n_accepted[c]) == int((want.passed == 1).sum())
+        assert int(got.last_passed[c]) == int(want.passed[-1])
+        assert int(got.last_bond_index[c]) == int(want.bond_index[-1])
+        assert rel_close(got.system_potential[c], want.system_potential[-1], RTOL64)
+        assert rel_close(got.nonbonded_potential[c], want.nonbonded_potential[-1], RTOL64)
+        assert rel_close(got.max_bond_distance[c], want.max_bond_distance[-1], RTOL64)
+        assert np.allclose(got.positions[c], want.final_positions, rtol=RTOL64, atol=1e-9)
+
+
+def test_batch_with_per_chain_positions_and_ragged_subunits():
+    # ragged subunits (1, 3, 17, 40 atoms), an atom in no subunit, subunit dict order != atom order
+    rng = np.random.default_rng(8)
+    sizes = [17, 1, 40, 3]
+    centres = np.array([[0, 0, 0], [9, 0, 0], [0, 11, 0], [0, 0, 8.0]])
+    coords, subunits, offset = [], {}, 0
+    for k, (size, centre) in enumerate(zip(sizes, centres)):
+        coords.append(centre + rng.normal(scale=1.8, size=(size, 3)))
+        subunits[10 - k] = list(range(offset, offset + size))[::-1]
+        offset += size
+    coords.append(np.array([[5.0, 5.0, 5.0]]))  # loose atom: static, still interacts
+    pos = np.concatenate(coords)
+    n = pos.shape[0]
+    mol = mch.Molecule(atoms=[mch.Atom(i, "C") for i in range(n)], bonds=[], position_matrix=pos)
+    long_bonds = ((16, 17), (57, 20), (0, 58), (18, 60))
+    steps = 60
+    chains = 3
+    positions = np.stack([pos + rng.normal(scale=0.05, size=pos.shape) for _ in range(chains)])
+    seeds = [5, 6, 7]
+    opt = mch.Optimizer(step_size=0.3, target_bond_length=1.5, num_steps=steps)
+    got = opt.get_results_batch(mol, long_bonds, subunits, seeds=seeds, positions=positions)
+    p = orc.OptimizerParams(step_size=0.3, target_bond_length=1.5, num_steps=steps)
+    for c in range(chains):
+        want = orc.optimizer_run(positions[c], long_bonds, subunits, p, np.random.default_rng(seeds[c]))
+        assert int(got.n_accepted[c]) == int((want.passed == 1).sum())
+        assert rel_close(got.system_potential[c], want.system_potential[-1], RTOL64)
+        assert np.allclose(got.positions[c], want.final_positions, rtol=RTOL64, atol=1e-9)
+
+
+def test_fp32_mode_tolerance_against_reference():
+    # fp32 fast mode: potentials within 1e-4 relative (north_star).  Trajectories may fork
+    # once an accept test lands within fp32 noise, so compare the common prefix of the
+    # accept sequence and require that prefix to be long.
+    for case in ("benzene_seed1000", "poc_graph_seed1000"):
+        g = load_golden(case)
+        opt = golden_optimizer(g, precision="fp32")
+        _, result = opt.get_trajectory(golden_molecule(g), golden_bonds(g), golden_subunits(g))
+        props = [p for _, p in result.get_steps_properties()]
+        passed = np.array([-1 if p["passed"] is None else int(p["passed"]) for p in props])
+        same = passed == g["passed"]
+        prefix = len(same) if same.all() else int(np.argmin(same))
+        assert prefix >= min(100, len(same)), f"{case}: fp32 accept sequence forked at step {prefix}"
+        u = np.array([p["system_potential"] for p in props])[:prefix]
+        unb = np.array([p["nonbonded_potential"] for p in props])[:prefix]
+        assert rel_close(u, g["system_potential"][:prefix], RTOL32)
+        assert rel_close(unb, g["nonbonded_potential"][:prefix], RTOL32)
+
+
+# ------------------------------------------------------------------------- properties at BASELINE size
+@pytest.mark.parametrize("precision,rtol,atol", [("fp64", 1e-9, 1e-9), ("fp32", 1e-4, 2e-4)])
+def test_full_size_cage_properties(precision, rtol, atol):
+    # BASELINE config 4 geometry (20 subunits x 50 atoms), fewer chains/steps than the bench
+    mol, long_bonds, subunits = synthetic.cube_cage()
+    chains, steps = 48, 120
+    opt = mch.Optimizer(step_size=0.25, target_bond_length=1.2, num_steps=steps, precision=precision)
+    seeds = list(range(chains))
+    got = opt.get_results_batch(mol, long_bonds, subunits, seeds=seeds)
+    start = mol.get_position_matrix()
+    assert got.positions.shape == (chains, 1000, 3)
+    assert np.all(got.n_accepted >= 1) and np.all(got.n_accepted <= steps - 1)
+    # step 0 evaluates every pair once; each move evaluates n_moving x (N - n_moving) pairs
+    assert np.all(got.pair_evals == 1000 * 999 // 2 + (steps - 1) * 50 * 950)
+    # 1. rigidity: every subunit moved as a rigid body (pure translation)
+    for ids in subunits.values():
+        delta = got.positions[:, ids, :] - start[ids]
+        assert np.abs(delta - delta[:, :1, :]).max() < atol
+    # 2. the potential carried incrementally through all steps equals a fresh evaluation
+    fresh = mch.Optimizer(0.25, 1.2, 2, precision="fp64")
+    for c in (0, chains // 2, chains - 1):
+        u, unb = fresh.compute_potential(mol.with_position_matrix(got.positions[c]), long_bonds)
+        assert np.isclose(got.system_potential[c], u, rtol=rtol, atol=0)
+        assert np.isclose(got.nonbonded_potential[c], unb, rtol=rtol, atol=0)
+    # 3. same seed -> same chain; different seeds -> different chains
+    again = opt.get_results_batch(mol, long_bonds, subunits, seeds=seeds[:4])
+    assert np.array_equal(again.positions, got.positions[:4])
+    assert len({float(u) for u in got.system_potential}) > chains // 2
+    # 4. the optimisation does optimise: the system potential drops, the longest bond does not grow
+    u0, _ = fresh.compute_potential(mol, long_bonds)
+    assert got.system_potential.mean() < 0.9 * u0
+    assert got.max_bond_distance.mean() < max(np.linalg.norm(start[a] - start[b]) for a, b in long_bonds)
+
+
+# ------------------------------------------------------------------------- Collapser
+@pytest.mark.parametrize("case", ["collapser_poc", "collapser_poc_noscale", "collapser_toy"])
+def test_collapser_matches_reference(case):
+    g = load_golden(case)
+    mol = golden_molecule(g)
+    coll = mch.Collapser(step_size=float(g["step_size"]), distance_threshold=float(g["distance_threshold"]),
+                         scale_steps=bool(g["scale_steps"]))
+    subunits, bonds = golden_subunits(g), golden_bonds(g)
+    out_mol, result = coll.get_trajectory(mol, bonds, subunits)
+    assert result.get_step_count() == int(g["steps_run"])
+    far = np.array([p["max_bond_distance"] for _, p in result.get_steps_properties()])
+    assert rel_close(far, g["max_bond_distance"], RTOL64)
+    frames = np.array([f for _, f in result.get_trajectory()])
+    assert np.allclose(frames, g["positions"], rtol=RTOL64, atol=1e-9)
+    assert np.allclose(out_mol.get_position_matrix(), g["final_positions"], rtol=RTOL64, atol=1e-9)
+    assert f"Steps run: {int(g['steps_run'])}\n" in result.get_log()
+    logged = float(result.get_log().split("Minimum inter-subunit distance: ")[1].split()[0])
+    assert rel_close(logged, float(g["min_distance_logged"]), RTOL64)
+    out_mol2, last = coll.get_result(mol, bonds, subunits)
+    assert last.step == int(g["steps_run"])
+    assert np.allclose(out_mol2.get_position_matrix(), g["final_positions"], rtol=RTOL64, atol=1e-9)
+    assert rel_close(last.max_bond_distance, g["max_bond_distance"][-1], RTOL64)
+
+
+def test_collapser_known_answers():
+    # reference tests/collapser/test_collapser.py:69-160
+    pos = np.array([[0, 1, 0], [1, 1, 0], [-1, 1, 0], [0, 10, 0], [1, 10, 0], [-1, 10, 0]])
+    bonds = [mch.Bond(0, (0, 1)), mch.Bond(1, (0, 2)), mch.Bond(2, (0, 3)), mch.Bond(3, (3, 4)), mch.Bond(4, (3, 5))]
+    mol = mch.Molecule(atoms=[mch.Atom(i, "C") for i in range(6)], bonds=bonds, position_matrix=pos)
+    coll = mch.Collapser(step_size=0.05, distance_threshold=1.5, scale_steps=True)
+    subunits = mol.get_subunits(bond_pair_ids=((0, 3),))
+    test_mol, results = coll.get_trajectory(mol=mol, bond_pair_ids=((0, 3),), subunits=subunits)
+    assert results.get_step_count() == 35
+    final_min = min(coll._get_subunit_distances(test_mol, subunits))
+    assert np.isclose(1.4947505, final_min, atol=1e-8)
+    want = np.array([[0.0, 4.75262477, 0.0], [1.0, 4.75262477, 0.0], [-1.0, 4.75262477, 0.0],
+                     [0.0, 6.24737523, 0.0], [1.0, 6.24737523, 0.0], [-1.0, 6.24737523, 0.0]])
+    assert np.allclose(test_mol.get_position_matrix(), want, atol=1e-8)
+
+
+def test_collapser_batch_with_hydrogens_against_oracle():
+    mol, long_bonds, subunits = synthetic.cube_cage(atoms_per_subunit=12, seed=9, spread=7.0, h_fraction=0.3)
+    rng = np.random.default_rng(2)
+    base = mol.get_position_matrix()
+    positions = np.stack([base * s for s in (1.0, 1.1, 1.25)])
+    is_h = [a.get_element_string() == "H" for a in mol.get_atoms()]
+    assert any(is_h)
+    coll = mch.Collapser(step_size=0.04, distance_threshold=1.4, scale_steps=True)
+    got = coll.get_results_batch(mol, long_bonds, subunits, positions)
+    for m in range(positions.shape[0]):
+        want = orc.collapser_run(positions[m], is_h, long_bonds, subunits, 0.04, 1.4, True)
+        assert int(got.steps_run[m]) == want.steps_run
+        assert rel_close(got.min_distance[m], want.min_distance, RTOL64)
+        assert np.allclose(got.positions[m], want.final_positions, rtol=RTOL64, atol=1e-9)
+        assert rel_close(got.max_bond_distance[m], want.max_bond_distance[-1], RTOL64)
+    del rng
+
+
+def test_collapser_never_touching_raises():
+    pos = np.array([[0.0, 0, 0], [1.5, 0, 0], [3.0, 0, 0]])
+    mol = mch.Molecule(atoms=[mch.Atom(i, "C") for i in range(3)], bonds=[], position_matrix=pos)
+    coll = mch.Collapser(step_size=0.05, distance_threshold=0.5, max_steps=50)
+    with pytest.raises(RuntimeError):
+        coll.get_result(mol, ((0, 1),), {0: [0, 1, 2]})
