@@ -1,0 +1,409 @@
+#!/usr/bin/env python
+"""bench.py -- MC chain-steps/s of the resident Metropolis kernel on the BASELINE workload.
+
+    python bench.py --gpus N --steps K --warmup W            (own arm, CUDA)
+    python bench.py --impl reference --gpus N --steps K ...  (CPU arm: the oracle port)
+
+Workload (BASELINE.json configs[3]): 4096 independent chains PER GPU of the synthetic
+1000-atom cube cage (20 rigid subunits x 50 atoms, 24 long bonds), Optimizer(step_size=0.25,
+target_bond_length=1.2, num_steps=500) with reference defaults otherwise, distinct seeds.
+One bench "step" = one launch of the whole batch = chains x (num_steps - 1) Monte-Carlo
+moves.  `value` = chain-steps/s with inputs resident in HBM; `e2e` = the same through
+Optimizer.prepare_batch(...).run(...) with host buffers (pinned H2D of per-chain positions +
+RNG states, D2H of final positions + per-chain scalars inside the timed region).
+"""
+
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+REPO = os.path.dirname(os.path.abspath(__file__))
+if REPO not in sys.path:
+    sys.path.insert(0, REPO)
+
+METRIC = "mc_chain_steps_per_s"
+UNIT = "chain-steps/s"
+FLOPS_PER_PAIR = 13.0  # 10 FP-pipe instructions (FMA = 2 flops) + 1 MUFU per pair, mu = 3
+WORKLOADS = {
+    # name: (builder, atoms, pairs per move)
+    "cube1000": dict(chains=4096, num_steps=500),
+    "m12l24": dict(chains=1024, num_steps=100),
+}
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="cuda", choices=["cuda", "reference"])
+    ap.add_argument("--workload", default="cube1000", choices=sorted(WORKLOADS))
+    ap.add_argument("--precision", default="fp32", choices=["fp32", "fp64"])
+    ap.add_argument("--chains", type=int, default=0, help="chains per GPU (default: workload's)")
+    ap.add_argument("--num-steps", type=int, default=0, help="Optimizer num_steps (default: workload's)")
+    ap.add_argument("--threads", type=int, default=0, help="threads per chain (0 = library default)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-seconds", type=float, default=12.0, help="CPU baseline budget per core")
+    ap.add_argument("--cpu-worker", action="store_true", help=argparse.SUPPRESS)
+    ap.add_argument("--cpu-moves", type=int, default=0, help=argparse.SUPPRESS)
+    ap.add_argument("--cpu-chains", type=int, default=0, help=argparse.SUPPRESS)
+    return ap.parse_args()
+
+
+def build_workload(name: str):
+    from mchammer_b200 import synthetic
+
+    if name == "cube1000":
+        return synthetic.cube_cage()
+    return synthetic.cuboctahedron_cage()
+
+
+# =====================================================================================
+# CPU arm: the oracle port (oracle/mch_oracle.py) on the host cores, one chain per process
+# =====================================================================================
+def _cpu_chain(job):
+    """One chain of `moves` Monte-Carlo moves through the oracle; returns seconds."""
+    import numpy as np
+
+    from oracle import mch_oracle as orc
+
+    pos, long_bonds, subunits, moves, seed = job
+    p = orc.OptimizerParams(step_size=0.25, target_bond_length=1.2, num_steps=moves + 1)
+    t0 = time.perf_counter()
+    orc.optimizer_run(pos, long_bonds, subunits, p, np.random.default_rng(seed))
+    return time.perf_counter() - t0
+
+
+def cpu_sample(workload: str, moves: int, chains: int, cores: int):
+    """Run `chains` oracle chains of `moves` moves over `cores` processes; wall seconds."""
+    import multiprocessing as mp
+
+    mol, long_bonds, subunits = build_workload(workload)
+    pos = mol.get_position_matrix()
+    jobs = [(pos, long_bonds, subunits, moves, 1000 + c) for c in range(chains)]
+    ctx = mp.get_context("fork")
+    with ctx.Pool(processes=cores) as pool:
+        pool.map(_cpu_chain, jobs[:cores])  # warm the workers (imports, first-call costs)
+        t0 = time.perf_counter()
+        per_chain = pool.map(_cpu_chain, jobs, chunksize=1)
+        wall = time.perf_counter() - t0
+    return wall, sum(per_chain)
+
+
+def cpu_worker_main(args):
+    """Child process entry (never imports torch, so fork() is safe)."""
+    cores = os.cpu_count() or 1
+    wall, busy = cpu_sample(args.workload, args.cpu_moves, args.cpu_chains, cores)
+    print(json.dumps({"wall": wall, "busy": busy, "cores": cores}))
+
+
+def run_cpu_subprocess(workload: str, moves: int, chains: int):
+    cmd = [sys.executable, os.path.abspath(__file__), "--cpu-worker", "--workload", workload,
+           "--cpu-moves", str(moves), "--cpu-chains", str(chains)]
+    env = dict(os.environ, OMP_NUM_THREADS="1", OPENBLAS_NUM_THREADS="1", MKL_NUM_THREADS="1")
+    out = subprocess.run(cmd, capture_output=True, text=True, env=env, timeout=1500)
+    if out.returncode != 0:
+        raise RuntimeError("cpu worker failed: " + out.stderr[-2000:])
+    return json.loads(out.stdout.strip().splitlines()[-1])
+
+
+def cpu_baseline(workload: str, budget_s: float):
+    """Oracle port on all host cores, bounded to about `budget_s` seconds per core."""
+    cores = os.cpu_count() or 1
+    n_atoms = 1000 if workload == "cube1000" else 5004
+    est_move_s = 1.0e-2 * (n_atoms / 1000.0) ** 2  # ~100 moves/s/core at N = 1000
+    moves = max(5, int(budget_s / est_move_s / 2))
+    chains = 2 * cores
+    r = run_cpu_subprocess(workload, moves, chains)
+    value = chains * moves / r["wall"]
+    return {
+        "value": value, "unit": UNIT, "cores": r["cores"], "kind": "port",
+        "sample": f"{chains} chains x {moves} moves of {workload} through oracle/mch_oracle.py "
+                  f"(numpy/scipy restatement of the reference), one chain per process on {r['cores']} cores, "
+                  f"{r['wall']:.1f} s wall; per-core rate {chains * moves / r['busy']:.1f} chain-steps/s",
+    }
+
+
+def reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    spec = WORKLOADS[args.workload]
+    cores = os.cpu_count() or 1
+    n_atoms = 1000 if args.workload == "cube1000" else 5004
+    est_move_s = 1.0e-2 * (n_atoms / 1000.0) ** 2
+    moves = max(3, int(1.0 / est_move_s))  # ~1 s of work per chain per bench step
+    chains = cores
+    total = args.steps + args.warmup
+    times = []
+    for k in range(total):
+        r = run_cpu_subprocess(args.workload, moves, chains)
+        if k >= args.warmup:
+            times.append(r["wall"])
+    seconds = sum(times)
+    value = args.steps * chains * moves / seconds
+    sample = (f"each step = {chains} chains x {moves} moves of {args.workload} through the oracle port, "
+              f"one chain per process on {cores} cores")
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * seconds / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+        "data": "synthetic",
+        "config": {"workload": f"{args.workload}: {spec['chains']} chains/GPU x {spec['num_steps']} num_steps "
+                               "(CPU arm runs a bounded sample of it)", "sample": sample},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+# =====================================================================================
+# clocks during the timed region
+# =====================================================================================
+class ClockSampler:
+    QUERY = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.rows, self.proc, self.thread = [], None, None
+        self.gpu_index = gpu_index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.gpu_index), f"--query-gpu={self.QUERY}",
+                 "--format=csv,noheader,nounits", "-lms", "100"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except OSError:
+            self.proc = None
+            return
+        self.thread = threading.Thread(target=self._pump, daemon=True)
+        self.thread.start()
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.perf_counter(), line.strip()))
+
+    def stop(self, t0: float, t1: float):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, smax, reasons, power = [], None, set(), []
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        inside = [r for t, r in self.rows if t0 <= t <= t1] or [r for _, r in self.rows]
+        for row in inside:
+            f = [x.strip() for x in row.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); smax = float(f[1]); power.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, flag in zip(names, f[3:7]):
+                if flag.lower().startswith("active"):
+                    reasons.add(name)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": smax,
+                "reasons": sorted(reasons), "samples": len(sm),
+                "power_w_max": max(power) if power else None}
+
+
+# =====================================================================================
+# own arm
+# =====================================================================================
+def measured_peaks():
+    path = os.path.join(REPO, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as fh:
+            return json.load(fh), "measured (MEASURED_PEAKS.json)"
+    return {"hbm_gbs": 6650.0}, "fallback (B200_PROFILING.md)"
+
+
+def probe_pipe_peak(torch, dtype_code: int, device) -> float:
+    """TFLOP/s of a pure dependent-FMA kernel (8 chains/thread) -- the arithmetic-pipe roofline."""
+    import ctypes as C
+
+    from mchammer_b200 import native
+
+    lib = native.lib()
+    sink = torch.zeros(1, dtype=torch.float32, device=device)
+    blocks, threads, iters = 148 * 8, 256, 1 << 15
+    stream = torch.cuda.current_stream(device).cuda_stream
+    best = 0.0
+    for _ in range(4):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        native.check(lib.mch_probe_fma(dtype_code, blocks, threads, iters, C.c_void_p(sink.data_ptr()),
+                                       C.c_void_p(stream)), "mch_probe_fma")
+        e1.record()
+        e1.synchronize()
+        ms = e0.elapsed_time(e1)
+        per_op = 1.0 if dtype_code == 2 else 2.0
+        best = max(best, per_op * 8.0 * iters * blocks * threads / (ms * 1e-3) / 1e12)
+    return best
+
+
+def cuda_arm(args):
+    import numpy as np
+    import torch
+
+    import mchammer_b200 as mch
+    from mchammer_b200 import native
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise native.NativeLibraryError("bench.py needs a CUDA device (no CPU fallback)")
+    torch.cuda.set_device(local)
+    device = torch.device("cuda", local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+
+        dist.init_process_group("nccl", device_id=device)
+
+    spec = WORKLOADS[args.workload]
+    chains = args.chains or spec["chains"]
+    num_steps = args.num_steps or spec["num_steps"]
+    mol, long_bonds, subunits = build_workload(args.workload)
+    n_atoms = mol.get_num_atoms()
+    opt = mch.Optimizer(step_size=0.25, target_bond_length=1.2, num_steps=num_steps,
+                        precision=args.precision, device=local)
+    plan = opt.prepare_batch(mol, long_bonds, subunits, chains, devices=[local],
+                             per_chain_positions=True, threads_per_chain=args.threads)
+    seeds = [1000 + rank * chains + c for c in range(chains)]
+    moves = num_steps - 1
+
+    # ---------------- device-resident timing (value, roofline)
+    plan.stage_inputs(seeds=seeds)
+    plan.upload()
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=device)  # > 126 MB L2
+    for _ in range(max(args.warmup, 3)):
+        plan.launch()
+    torch.cuda.synchronize()
+    if dist is not None:
+        dist.barrier()
+    sampler = ClockSampler(local)
+    sampler.start()
+    time.sleep(0.25)
+    events = []
+    t_begin = time.perf_counter()
+    torch.cuda.synchronize()
+    for _ in range(args.steps):
+        flush.zero_()  # untimed: evict the previous step's lines from L2
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        plan.launch()
+        e1.record()
+        events.append((e0, e1))
+    torch.cuda.synchronize()
+    t_end = time.perf_counter()
+    kernel_ms = [a.elapsed_time(b) for a, b in events]
+    dev_seconds = sum(kernel_ms) * 1e-3
+    pairs_per_launch = int(plan.shards[0].out.pair_evals.sum().item())
+
+    # ---------------- end to end through the public API (host buffers in, host buffers out)
+    host_positions = plan.h_pos_in  # pinned [C,N,3]; per-chain start geometries
+    rng_words = mch.rngstate.seed_states(seeds)
+    for _ in range(2):
+        plan.run(rng_words=rng_words, positions=host_positions)
+    if dist is not None:
+        dist.barrier()
+    torch.cuda.synchronize()
+    e2e_t0 = time.perf_counter()
+    h2d = d2h = 0
+    for _ in range(args.steps):
+        res = plan.run(rng_words=rng_words, positions=host_positions)
+        h2d, d2h = res.h2d_bytes, res.d2h_bytes
+    torch.cuda.synchronize()
+    e2e_seconds = time.perf_counter() - e2e_t0
+    clocks = sampler.stop(t_begin, time.perf_counter())
+    accepted = float(res.n_accepted.mean())
+
+    # ---------------- reduce over ranks: slowest rank sets the time
+    if dist is not None:
+        t = torch.tensor([dev_seconds, e2e_seconds], dtype=torch.float64, device=device)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dev_seconds, e2e_seconds = float(t[0]), float(t[1])
+    total_chain_steps = args.steps * chains * moves * world
+    value = total_chain_steps / dev_seconds
+    e2e_value = total_chain_steps / e2e_seconds
+
+    if rank == 0:
+        peaks, peaks_src = measured_peaks()
+        dtype_code = native.MCH_F32 if args.precision == "fp32" else native.MCH_F64
+        pipe_peak = probe_pipe_peak(torch, dtype_code, device)
+        mufu_peak = probe_pipe_peak(torch, 2, device) if args.precision == "fp32" else None
+        launch_s = dev_seconds / args.steps
+        achieved_tflops = FLOPS_PER_PAIR * pairs_per_launch / launch_s / 1e12
+        io_bytes = chains * n_atoms * 3 * 8 * 2 + chains * 48 * 2
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": 1e3 * dev_seconds / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32" if args.precision == "fp32" else "f64", "data": "synthetic",
+            "config": {
+                "workload": f"{args.workload}: {chains} chains/GPU x {n_atoms} atoms "
+                            f"({len(subunits)} subunits, {len(long_bonds)} long bonds), num_steps={num_steps}, "
+                            f"seeds 1000+c, identical start geometry per chain",
+                "chains_per_gpu": chains, "num_steps": num_steps, "precision": args.precision,
+                "io_dtype": "f64", "l2": "flushed between timed steps (256 MiB memset, untimed)",
+                "threads_per_chain": args.threads or "auto",
+            },
+            "pair_evals_per_s": pairs_per_launch * world / launch_s,
+            "reference_equivalent_pair_evals_per_s": value * (n_atoms * (n_atoms - 1) // 2),
+            "accepted_moves_per_chain": accepted,
+            "roofline": {
+                "bound": "fp32_pipe" if args.precision == "fp32" else "fp64_pipe",
+                "achieved": achieved_tflops, "peak": pipe_peak, "unit": "TFLOP/s",
+                "frac": achieved_tflops / pipe_peak if pipe_peak else None,
+                "traffic": None,
+                "kernel": "mch_optimize_kernel",
+                "note": f"achieved = {FLOPS_PER_PAIR:.0f} flops/pair x {pairs_per_launch} pairs per launch / "
+                        "CUDA-event launch time; peak = dependent-FMA probe (mch_probe_fma) measured in this run; "
+                        "the kernel is bound by the CUDA-core FP pipe, not by HBM or tensor cores (SURVEY.md 8-d)",
+                "mufu_rsqrt_per_s_peak": mufu_peak * 1e12 if mufu_peak else None,
+                "hbm": {"achieved_gbs": io_bytes / launch_s / 1e9, "peak_gbs": peaks.get("hbm_gbs"),
+                        "peak_source": peaks_src},
+            },
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "api": "Optimizer.prepare_batch(...).run(rng_words, positions) with pinned host buffers"},
+            "gpu_launches": args.steps,
+            "clocks": clocks,
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            line["cpu_baseline"] = cpu_baseline(args.workload, args.cpu_seconds)
+        else:
+            line["cpu_baseline"] = None
+        print(json.dumps(line))
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse_args()
+    if args.cpu_worker:
+        cpu_worker_main(args)
+    elif args.impl == "reference":
+        reference_arm(args)
+    else:
+        cuda_arm(args)
+
+
+if __name__ == "__main__":
+    main()

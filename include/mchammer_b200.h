@@ -151,6 +151,12 @@ int mch_pcg64_stream_check(uint64_t* rng_state /* [6] in/out */, int rounds, uin
 int mch_probe_fma(int dtype, int blocks, int threads, int iters, float* sink /* [dev] [1] */,
                   void* stream);
 
+/* Ceiling probe for the fp32 pair sweep: every CTA runs `iters` sweeps of n_rows x n_cols pair
+ * terms (the Monte-Carlo kernel's inner tile loop, no control section); with_barrier adds the
+ * per-sweep __syncthreads().  n_rows*n_cols*iters*blocks pair terms per launch. */
+int mch_probe_sweep(int blocks, int threads, int iters, int with_barrier, int n_rows, int n_cols,
+                    float* sink /* [dev] [1] */, void* stream);
+
 const char* mch_last_error(void);
 int mch_version(void);
 

@@ -8,7 +8,8 @@ calling a driver without CUDA or without the built library raises.
 
 from .collapser import CollapseBatchResult, Collapser
 from .elements import get_radius
-from .optimizer import BatchResult, Optimizer, shard_bounds
+from .batch import BatchPlan, BatchResult, shard_bounds
+from .optimizer import Optimizer
 from .primitives import (
     get_atom_distance,
     get_bond_vector,
@@ -39,6 +40,7 @@ __all__ = [
     "rotate_molecule_by_angle",
     "rotation_matrix_arbitrary_axis",
     # additions of this framework
+    "BatchPlan",
     "BatchResult",
     "CollapseBatchResult",
     "shard_bounds",

@@ -1,0 +1,208 @@
+"""Batched Metropolis chains: a prepared plan that owns pinned host staging buffers and the
+per-device buffers, so repeated runs pay only H2D copy + kernel + D2H copy.
+
+Independent chains shard contiguously over the devices of one box; there is no collective
+and no peer traffic on the data path.  One host thread drives all
+devices: copies and launches are asynchronous on each device's current stream, results
+are read back device by device.
+"""
+
+from __future__ import annotations
+
+import time
+from dataclasses import dataclass
+from typing import Sequence
+
+import numpy as np
+
+from . import engine, native, rngstate
+from .lowering import LoweredTopology
+
+
+@dataclass
+class BatchResult:
+    """Outcome of ``C`` independent chains (host arrays)."""
+
+    positions: np.ndarray            # [C,N,3]
+    system_potential: np.ndarray     # [C]
+    nonbonded_potential: np.ndarray  # [C]
+    max_bond_distance: np.ndarray    # [C]
+    n_accepted: np.ndarray           # [C] accepted moves
+    last_passed: np.ndarray          # [C] 1/0; -1 when no move was made
+    last_bond_index: np.ndarray      # [C] index into bond_pair_ids; -1 when no move
+    pair_evals: np.ndarray           # [C] pair terms the kernel evaluated
+    num_steps: int
+    seconds: float                   # wall time of the call (H2D + kernel + D2H)
+    h2d_bytes: int = 0
+    d2h_bytes: int = 0
+
+    def __len__(self) -> int:
+        return int(self.positions.shape[0])
+
+    def molecule(self, index: int, template):
+        return template.with_position_matrix(np.array(self.positions[index], dtype=np.float64))
+
+    def copy(self) -> "BatchResult":
+        fields = {k: (v.copy() if isinstance(v, np.ndarray) else v) for k, v in self.__dict__.items()}
+        return BatchResult(**fields)
+
+
+def unpack_info(info: np.ndarray):
+    """Split trace words: bond | passed << 16 | kind << 17 | moved subunit << 18 (-1: no move)."""
+    info = np.asarray(info, dtype=np.int64)
+    none = info < 0
+    bond = np.where(none, -1, info & 0xFFFF)
+    passed = np.where(none, -1, (info >> 16) & 1)
+    kind = np.where(none, -1, (info >> 17) & 1)
+    moved = np.where(none, -1, (info >> 18) & 0x1FFF)
+    return bond, passed, kind, moved
+
+
+def shard_bounds(n_items: int, n_shards: int) -> list[tuple[int, int]]:
+    """Contiguous, balanced ``[lo, hi)`` ranges: shard ``g`` gets items ``g*n/G .. (g+1)*n/G``."""
+    if n_shards <= 0:
+        raise ValueError("n_shards must be positive")
+    return [((g * n_items) // n_shards, ((g + 1) * n_items) // n_shards) for g in range(n_shards)]
+
+
+class _Shard:
+    """Buffers of one device."""
+
+    def __init__(self, torch, topo: LoweredTopology, device_index: int, lo: int, hi: int,
+                 io_torch_dtype, per_chain_positions: bool):
+        self.lo, self.hi, self.count = lo, hi, hi - lo
+        self.device = torch.device("cuda", device_index)
+        n = topo.n_atoms
+        with torch.cuda.device(self.device):
+            self.dtopo = engine.upload_topology(topo, device_index)
+            rows = self.count if per_chain_positions else 1
+            self.pos_in = torch.empty((rows, n, 3), dtype=io_torch_dtype, device=self.device)
+            self.rng = torch.empty((self.count, 6), dtype=torch.int64, device=self.device)
+            self.out = None  # engine.OptimizeOutput, allocated by the first launch and reused
+
+
+class BatchPlan:
+    """Prepared batched run of one topology: ``plan.run(seeds, positions)`` -> BatchResult.
+
+    The arrays of the returned BatchResult are views of this plan's pinned host buffers
+    and are overwritten by the next ``run``; call ``.copy()`` to keep them.
+    """
+
+    def __init__(self, topo: LoweredTopology, base_positions: np.ndarray, params, num_steps: int,
+                 precision: str, n_chains: int, devices: Sequence[int], io_dtype=np.float64,
+                 per_chain_positions: bool = False, threads_per_chain: int = 0):
+        torch = native.require_cuda()
+        native.lib()
+        self._torch = torch
+        self.topo = topo
+        self.params = params
+        self.num_steps = max(int(num_steps), 1)
+        self.precision = precision
+        self.n_chains = int(n_chains)
+        self.threads_per_chain = int(threads_per_chain)
+        self.per_chain_positions = bool(per_chain_positions)
+        self.io_dtype = np.dtype(io_dtype)
+        if self.io_dtype not in (np.dtype(np.float64), np.dtype(np.float32)):
+            raise TypeError("io_dtype must be float64 or float32")
+        tdtype = torch.float64 if self.io_dtype == np.float64 else torch.float32
+        n = topo.n_atoms
+        c = self.n_chains
+
+        def pinned(shape, dtype):
+            return torch.empty(shape, dtype=dtype).pin_memory()
+
+        # pinned host staging: inputs ...
+        self.h_pos_in = pinned((c if per_chain_positions else 1, n, 3), tdtype)
+        self.h_rng = pinned((c, 6), torch.int64)
+        # ... and outputs
+        self.h_pos_out = pinned((c, n, 3), tdtype)
+        self.h_f64 = pinned((3, c), torch.float64)   # U, U_nb, max bond
+        self.h_i32 = pinned((2, c), torch.int32)     # n_accepted, last_step_info
+        self.h_pairs = pinned((c,), torch.int64)
+        self.h_pos_in[0].copy_(torch.from_numpy(np.ascontiguousarray(base_positions, dtype=self.io_dtype)))
+        if per_chain_positions:
+            self.h_pos_in[:] = self.h_pos_in[0]
+        self.shards = [
+            _Shard(torch, topo, dev, lo, hi, tdtype, per_chain_positions)
+            for dev, (lo, hi) in zip(devices, shard_bounds(c, len(devices))) if hi > lo
+        ]
+
+    # -- the three phases, separately callable so a benchmark can time the device part alone
+    def stage_inputs(self, seeds: Sequence[int] | None = None, positions=None,
+                     rng_words: np.ndarray | None = None) -> int:
+        """Fill the pinned input buffers on the host.  Returns the bytes that will go H2D."""
+        torch = self._torch
+        if rng_words is None:
+            if seeds is None:
+                raise ValueError("give seeds or rng_words")
+            if len(seeds) != self.n_chains:
+                raise ValueError(f"expected {self.n_chains} seeds, got {len(seeds)}")
+            rng_words = rngstate.seed_states(seeds)
+        self.h_rng.copy_(torch.from_numpy(np.ascontiguousarray(rng_words, dtype=np.uint64).view(np.int64)))
+        if positions is not None:
+            if not self.per_chain_positions:
+                raise ValueError("this plan was prepared without per-chain positions")
+            src = positions if torch.is_tensor(positions) else torch.from_numpy(
+                np.ascontiguousarray(positions, dtype=self.io_dtype))
+            if tuple(src.shape) != tuple(self.h_pos_in.shape):
+                raise ValueError(f"positions must be {tuple(self.h_pos_in.shape)}, got {tuple(src.shape)}")
+            if src.data_ptr() != self.h_pos_in.data_ptr():
+                self.h_pos_in.copy_(src)
+        return self.h_rng.numel() * 8 + self.h_pos_in.numel() * self.h_pos_in.element_size()
+
+    def upload(self) -> None:
+        torch = self._torch
+        for sh in self.shards:
+            with torch.cuda.device(sh.device):
+                if self.per_chain_positions:
+                    sh.pos_in.copy_(self.h_pos_in[sh.lo:sh.hi], non_blocking=True)
+                else:
+                    sh.pos_in.copy_(self.h_pos_in, non_blocking=True)
+                sh.rng.copy_(self.h_rng[sh.lo:sh.hi], non_blocking=True)
+
+    def launch(self) -> None:
+        torch = self._torch
+        for sh in self.shards:
+            with torch.cuda.device(sh.device):
+                sh.out = engine.optimize_on_device(
+                    sh.dtopo, sh.pos_in, sh.count, sh.rng, self.params, self.num_steps,
+                    self.precision, threads_per_chain=self.threads_per_chain, out=sh.out,
+                )
+
+    def download(self) -> int:
+        """Device -> pinned host (async per device), then wait.  Returns the bytes read back."""
+        torch = self._torch
+        for sh in self.shards:
+            with torch.cuda.device(sh.device):
+                o = sh.out
+                self.h_pos_out[sh.lo:sh.hi].copy_(o.positions, non_blocking=True)
+                self.h_f64[0, sh.lo:sh.hi].copy_(o.system_potential, non_blocking=True)
+                self.h_f64[1, sh.lo:sh.hi].copy_(o.nonbonded_potential, non_blocking=True)
+                self.h_f64[2, sh.lo:sh.hi].copy_(o.max_bond_distance, non_blocking=True)
+                self.h_i32[0, sh.lo:sh.hi].copy_(o.n_accepted, non_blocking=True)
+                self.h_i32[1, sh.lo:sh.hi].copy_(o.last_step_info, non_blocking=True)
+                self.h_pairs[sh.lo:sh.hi].copy_(o.pair_evals, non_blocking=True)
+        for sh in self.shards:
+            torch.cuda.current_stream(sh.device).synchronize()
+        return (self.h_pos_out.numel() * self.h_pos_out.element_size() + self.h_f64.numel() * 8
+                + self.h_i32.numel() * 4 + self.h_pairs.numel() * 8)
+
+    def result(self, seconds: float = 0.0, h2d: int = 0, d2h: int = 0) -> BatchResult:
+        bond, passed, _, _ = unpack_info(self.h_i32[1].numpy())
+        return BatchResult(
+            positions=self.h_pos_out.numpy(),
+            system_potential=self.h_f64[0].numpy(), nonbonded_potential=self.h_f64[1].numpy(),
+            max_bond_distance=self.h_f64[2].numpy(), n_accepted=self.h_i32[0].numpy().astype(np.int64),
+            last_passed=passed, last_bond_index=bond, pair_evals=self.h_pairs.numpy(),
+            num_steps=self.num_steps, seconds=seconds, h2d_bytes=h2d, d2h_bytes=d2h,
+        )
+
+    def run(self, seeds: Sequence[int] | None = None, positions=None,
+            rng_words: np.ndarray | None = None) -> BatchResult:
+        """Host buffers in, host buffers out: stage -> H2D -> kernel -> D2H."""
+        start = time.perf_counter()
+        h2d = self.stage_inputs(seeds, positions, rng_words)
+        self.upload()
+        self.launch()
+        d2h = self.download()
+        return self.result(time.perf_counter() - start, h2d, d2h)

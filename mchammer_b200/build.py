@@ -17,9 +17,9 @@ import sys
 PKG = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(PKG, "csrc")
 LIB = os.path.join(PKG, "libmchammer_b200.so")
-SOURCES = ["mch_api.cu"]
+SOURCES = ["mch_api.cu", "mch_optimize_f32.cu", "mch_optimize_f64.cu"]
 HEADERS = [
-    "mch_device.cuh", "mch_optimize.cuh", "mch_potential.cuh", "mch_collapse.cuh",
+    "mch_device.cuh", "mch_optimize.cuh", "mch_potential.cuh", "mch_collapse.cuh", "mch_host.h",
     os.path.join("..", "..", "include", "mchammer_b200.h"),
 ]
 
@@ -27,7 +27,7 @@ NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-lineinfo", "-O3", "-std=c++17",
     "-ftz=true",  # fp32 rsqrtf -> a single MUFU.RSQ; fp64 arithmetic is unaffected
-    "-shared", "-Xcompiler", "-fPIC",
+    "-Xcompiler", "-fPIC",
 ]
 
 
@@ -46,21 +46,43 @@ def is_stale() -> bool:
     return any(os.path.getmtime(d) > built for d in deps)
 
 
-def build_library(force: bool = False, verbose: bool = False) -> str:
-    if not force and not is_stale():
+def build_library(force: bool = False, verbose: bool = False, defines=(), out: str | None = None) -> str:
+    """Compile every translation unit (in parallel) and link them into the shared library.
+
+    ``defines``/``out`` build a tuning variant (``-DNAME=VALUE`` ...) into another file; the
+    default build has no defines and goes to libmchammer_b200.so.
+    """
+    if out is None and not defines and not force and not is_stale():
         return LIB
-    cmd = [_nvcc(), *NVCC_FLAGS]
-    if verbose:
-        cmd += ["-Xptxas", "-v"]
-    cmd += ["-o", LIB, *[os.path.join(CSRC, s) for s in SOURCES]]
-    proc = subprocess.run(cmd, capture_output=True, text=True)
-    if verbose:
-        sys.stderr.write(proc.stderr)
+    target = out or LIB
+    tag = "_".join(d.replace("=", "-") for d in defines)
+    objdir = os.path.join(PKG, "build", tag) if tag else os.path.join(PKG, "build")
+    os.makedirs(objdir, exist_ok=True)
+    jobs = []
+    for src in SOURCES:
+        obj = os.path.join(objdir, os.path.splitext(src)[0] + ".o")
+        cmd = [_nvcc(), *NVCC_FLAGS, *[f"-D{d}" for d in defines], "-c", "-o", obj, os.path.join(CSRC, src)]
+        if verbose:
+            cmd[1:1] = ["-Xptxas", "-v"]
+        jobs.append((cmd, obj, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
+    objects = []
+    for cmd, obj, proc in jobs:
+        out, _ = proc.communicate()
+        if verbose:
+            sys.stderr.write(out)
+        if proc.returncode != 0:
+            raise RuntimeError("nvcc failed:\n" + " ".join(cmd) + "\n" + out)
+        objects.append(obj)
+    link = [_nvcc(), "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-o", target, *objects]
+    proc = subprocess.run(link, capture_output=True, text=True)
     if proc.returncode != 0:
-        raise RuntimeError("nvcc failed:\n" + " ".join(cmd) + "\n" + proc.stdout + proc.stderr)
-    return LIB
+        raise RuntimeError("link failed:\n" + " ".join(link) + "\n" + proc.stdout + proc.stderr)
+    return target
 
 
 if __name__ == "__main__":
-    path = build_library(force="--force" in sys.argv, verbose="-v" in sys.argv)
+    defs = [a[2:] for a in sys.argv[1:] if a.startswith("-D")]
+    outs = [a[6:] for a in sys.argv[1:] if a.startswith("--out=")]
+    path = build_library(force="--force" in sys.argv, verbose="-v" in sys.argv, defines=defs,
+                         out=outs[0] if outs else None)
     print(path)

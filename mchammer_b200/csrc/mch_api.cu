@@ -10,13 +10,15 @@
 
 #include "mch_collapse.cuh"
 #include "mch_device.cuh"
+#include "mch_host.h"
 #include "mch_optimize.cuh"
 #include "mch_potential.cuh"
 
 namespace {
-
 thread_local char g_error[512] = "";
+}
 
+namespace mch {
 int fail(int code, const char* fmt, ...) {
   va_list ap;
   va_start(ap, fmt);
@@ -24,6 +26,11 @@ int fail(int code, const char* fmt, ...) {
   va_end(ap);
   return code;
 }
+}  // namespace mch
+
+namespace {
+using mch::fail;
+using mch::launch;
 
 constexpr int kMaxSmem = 227 * 1024;
 
@@ -63,26 +70,6 @@ int check_threads(int requested, int n_atoms, int* out) {
   if (t % 32 != 0 || t < 32 || t > 256) return fail(MCH_ERR_INVALID, "threads must be a multiple of 32 in [32, 256], got %d", t);
   *out = t;
   return MCH_OK;
-}
-
-template <typename K, typename A>
-int launch(K kernel, const A& args, int blocks, int threads, int smem, cudaStream_t stream, const char* what) {
-  cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-  if (e != cudaSuccess) return fail(MCH_ERR_CUDA, "%s: cudaFuncSetAttribute(%d B): %s", what, smem, cudaGetErrorString(e));
-  kernel<<<blocks, threads, smem, stream>>>(args);
-  e = cudaGetLastError();
-  if (e != cudaSuccess) return fail(MCH_ERR_CUDA, "%s: launch failed: %s", what, cudaGetErrorString(e));
-  return MCH_OK;
-}
-
-// dispatch helpers: compute type x io type x mu kind
-template <typename T, typename Tio>
-int launch_optimize_mu(int mk, const mch::OptArgs& a, int threads, int smem, cudaStream_t s) {
-  switch (mk) {
-    case mch::MU_3: return launch(mch::mch_optimize_kernel<T, Tio, mch::MU_3>, a, a.C, threads, smem, s, "mch_optimize_batch");
-    case mch::MU_INT: return launch(mch::mch_optimize_kernel<T, Tio, mch::MU_INT>, a, a.C, threads, smem, s, "mch_optimize_batch");
-    default: return launch(mch::mch_optimize_kernel<T, Tio, mch::MU_REAL>, a, a.C, threads, smem, s, "mch_optimize_batch");
-  }
 }
 
 template <typename T, typename Tio>
@@ -207,12 +194,9 @@ int mch_optimize_batch(const mch_optimize_desc* d, void* stream) {
   a.pairs = reinterpret_cast<unsigned long long*>(d->pair_evals);
   a.inexact_undo = d->inexact_undo;
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
-  if (d->compute_dtype == MCH_F64) {
-    return d->io_dtype == MCH_F64 ? launch_optimize_mu<double, double>(mk, a, threads, smem, s)
-                                  : launch_optimize_mu<double, float>(mk, a, threads, smem, s);
-  }
-  return d->io_dtype == MCH_F64 ? launch_optimize_mu<float, double>(mk, a, threads, smem, s)
-                                : launch_optimize_mu<float, float>(mk, a, threads, smem, s);
+  const bool io_f64 = d->io_dtype == MCH_F64;
+  return d->compute_dtype == MCH_F64 ? mch::launch_optimize_f64(io_f64, mk, a, threads, smem, s)
+                                     : mch::launch_optimize_f32(io_f64, mk, a, threads, smem, s);
 }
 
 int mch_potential_batch(const void* pos, int io_dtype, int compute_dtype, int n_mol, int n_atoms,
@@ -324,6 +308,15 @@ int mch_probe_fma(int dtype, int blocks, int threads, int iters, float* sink, vo
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return fail(MCH_ERR_CUDA, "mch_probe_fma: %s", cudaGetErrorString(e));
   return MCH_OK;
+}
+
+int mch_probe_sweep(int blocks, int threads, int iters, int with_barrier, int n_rows, int n_cols, float* sink, void* stream) {
+  if (blocks <= 0 || threads < 32 || threads > 256 || threads % 32 || iters <= 0 || n_rows < 1 || n_rows > 60 ||
+      n_cols < 1 || n_cols > 950 || !sink)
+    return fail(MCH_ERR_INVALID, "mch_probe_sweep: bad arguments");
+  const int rc = mch::launch_probe_sweep(blocks, threads, iters, with_barrier, n_rows, n_cols, sink,
+                                         reinterpret_cast<cudaStream_t>(stream));
+  return rc == 0 ? MCH_OK : fail(MCH_ERR_CUDA, "mch_probe_sweep: launch failed");
 }
 
 }  // extern "C"

@@ -61,7 +61,7 @@ struct OptArgs {
 
 // Shared-memory carve-up, identical on host (size query) and device.
 struct OptLayout {
-  int x, y, z, colsum, rows, E, csum, wsum, suoff, bslot, bsu, ctl, total;
+  int x, y, z, colsum, colsum_stride, rows, E, erow, csum, invn, wsum, suoff, bslot, bsu, ctl, total;
 };
 
 MCH_HD int align_up(int v, int a) { return (v + a - 1) / a * a; }
@@ -73,12 +73,14 @@ MCH_HD OptLayout opt_layout(int N, int S, int B, int max_su, int tsize) {
   L.x = o; o += np * tsize;
   L.y = o; o += np * tsize;
   L.z = o; o += np * tsize;
-  L.colsum = o; o += np * (tsize < 4 ? 4 : tsize);
+  L.colsum = o; L.colsum_stride = np * (tsize < 4 ? 4 : tsize); o += 2 * L.colsum_stride;  // double buffered
   o = align_up(o, 32);
-  L.rows = o; o += align_up(max_su, 2) * 4 * tsize;
+  L.rows = o; o += (max_su + 4) * 4 * tsize;  // + far-away padding row + prefetch overrun
   o = align_up(o, 16);
   L.E = o; o += S * S * 8;
-  L.csum = o; o += S * 3 * 8;
+  L.erow = o; o += S * 8;
+  L.csum = o; o += (S + 1) * 3 * 8;  // per-subunit coordinate sums + the molecule's
+  L.invn = o; o += S * 8;
   L.wsum = o; o += 3 * 32 * 8;
   L.suoff = o; o += align_up(S + 1, 4) * 4;
   L.bslot = o; o += align_up(2 * B, 4) * 4;
@@ -92,6 +94,7 @@ struct Ctl {
   int nrows;
   int c0, g0, g1, c1;
   int ms;
+  int buf;  // which column-sum buffer this sweep writes
 };
 
 #ifdef __CUDACC__
@@ -103,8 +106,21 @@ template <typename Tio> MCH_D void store_io(void* base, long long idx, double v)
   reinterpret_cast<Tio*>(base)[idx] = (Tio)v;
 }
 
-template <typename T, typename Tio, int MUK>
-__global__ void __launch_bounds__(256)
+// Subunits up to this many atoms are re-summed one lane per subunit when the energy table is
+// refreshed; larger ones by the whole warp.
+constexpr int REGROUP_SMALL = 64;
+
+#ifndef MCH_F32_THREADS_PER_SM
+#define MCH_F32_THREADS_PER_SM 1024
+#endif
+
+// NTMAX: largest block this instantiation may be launched with.  fp32: 1024 / NTMAX blocks
+// per SM caps the kernel at 64 registers per thread, i.e. 32 resident warps per SM, so the
+// control section of one chain (a single warp, latency bound) is covered by the pair sweeps
+// of the other resident chains.  fp64 needs twice the registers for the same column tile
+// (128 per thread, 16 resident warps).
+template <typename T, typename Tio, int MUK, int NTMAX>
+__global__ void __launch_bounds__(NTMAX, (sizeof(T) == 4 ? MCH_F32_THREADS_PER_SM : 512) / NTMAX)
 mch_optimize_kernel(const __grid_constant__ OptArgs a) {
   extern __shared__ __align__(32) unsigned char smem[];
   const int c = blockIdx.x;
@@ -116,10 +132,14 @@ mch_optimize_kernel(const __grid_constant__ OptArgs a) {
   T* X = reinterpret_cast<T*>(smem + L.x);
   T* Y = reinterpret_cast<T*>(smem + L.y);
   T* Z = reinterpret_cast<T*>(smem + L.z);
-  T* colsum = reinterpret_cast<T*>(smem + L.colsum);
+  T* colsum = reinterpret_cast<T*>(smem + L.colsum);  // buffer 0; buffer 1 follows
+  const int colsum_stride = L.colsum_stride / (int)sizeof(T);
   Row4<T>* Q = reinterpret_cast<Row4<T>*>(smem + L.rows);
   double* E = reinterpret_cast<double*>(smem + L.E);
+  double* erow = reinterpret_cast<double*>(smem + L.erow);  // erow[s] = sum_t E[s][t]
   double* csum = reinterpret_cast<double*>(smem + L.csum);
+  double* ctot = csum + 3 * S;  // coordinate sums of the whole molecule
+  double* invn = reinterpret_cast<double*>(smem + L.invn);
   double* wsum = reinterpret_cast<double*>(smem + L.wsum);   // 3 x 32: [0..31] cross, [32..63] intra
   int* suoff = reinterpret_cast<int*>(smem + L.suoff);
   int* bslot = reinterpret_cast<int*>(smem + L.bslot);
@@ -167,24 +187,30 @@ mch_optimize_kernel(const __grid_constant__ OptArgs a) {
     Z[n] = (T)(load_io<Tio>(a.pos_in, src + 2) - origin[2]);
   }
   for (int k = tid; k < S * S; k += nt) E[k] = 0.0;
+  for (int k = tid; k < S; k += nt) invn[k] = 1.0 / (double)(suoff[k + 1] - suoff[k]);
   __syncthreads();
 
   // ---------------------------------------------------------------- control-warp state
   // (uniform across the 32 lanes of warp 0; other warps never read it)
+  constexpr bool kFast = sizeof(T) == 4;  // fp32 mode: cheaper centroid bookkeeping
   Pcg64 rng = pcg_load(a.rng + 6LL * c);
   double U = 0.0, Unb = 0.0, Ub_trial = 0.0, e_intra = 0.0;
   T tvx = (T)0, tvy = (T)0, tvz = (T)0;
   int ms = 0, kb = 0, kind = 0, n_acc = 0, info = -1;
   unsigned long long pair_count = 0ULL;
 
-  auto fill_rows = [&](int s, T dx, T dy, T dz) {  // Q = P[s] - d ; warp 0 only
-    const int r0 = suoff[s], n = suoff[s + 1] - r0;
-    for (int i = lane; i < n; i += 32) {
+  // Q = P[s] - d, padded with far-away rows to an odd count (see sweep_tile); warp 0 only.
+  // Returns the padded count.
+  auto fill_rows = [&](int s, T dx, T dy, T dz) {
+    const int r0 = suoff[s], n = suoff[s + 1] - r0, np = padded_rows(n);
+    for (int i = lane; i < np; i += 32) {
       Row4<T> q;
-      q.x = X[r0 + i] - dx; q.y = Y[r0 + i] - dy; q.z = Z[r0 + i] - dz; q.w = (T)0;
+      if (i < n) { q.x = X[r0 + i] - dx; q.y = Y[r0 + i] - dy; q.z = Z[r0 + i] - dz; }
+      else { q.x = far_away<T>(); q.y = far_away<T>(); q.z = far_away<T>(); }
+      q.w = (T)0;
       Q[i] = q;
     }
-    return n;
+    return np;
   };
   auto refresh_csum = [&](int s) {  // coordinate sums of subunit s from current positions
     const int r0 = suoff[s], r1 = suoff[s + 1];
@@ -192,6 +218,12 @@ mch_optimize_kernel(const __grid_constant__ OptArgs a) {
     for (int i = r0 + lane; i < r1; i += 32) { sx += (double)X[i]; sy += (double)Y[i]; sz += (double)Z[i]; }
     sx = warp_sum(sx); sy = warp_sum(sy); sz = warp_sum(sz);
     if (lane == 0) { csum[3 * s] = sx; csum[3 * s + 1] = sy; csum[3 * s + 2] = sz; }
+  };
+  auto refresh_ctot = [&]() {  // molecule sums = sum of the subunit sums (fixed order)
+    double tx = 0.0, ty = 0.0, tz = 0.0;
+    for (int s = lane; s < S; s += 32) { tx += csum[3 * s]; ty += csum[3 * s + 1]; tz += csum[3 * s + 2]; }
+    tx = warp_sum(tx); ty = warp_sum(ty); tz = warp_sum(tz);
+    if (lane == 0) { ctot[0] = tx; ctot[1] = ty; ctot[2] = tz; }
   };
   // bond energy sum and longest bond; ends inside subunit `moved` are displaced by -tv
   auto bond_terms = [&](int moved, T dx, T dy, T dz, double& longest) {
@@ -220,8 +252,50 @@ mch_optimize_kernel(const __grid_constant__ OptArgs a) {
       if (a.trace_i) a.trace_i[(long long)c * a.num_steps + step] = info;
     }
   };
-  // Draw the next move exactly as optimizer.py:214-244 does and publish the sweep.
-  auto propose = [&]() {
+  // Row/column `row` of the energy table from the per-column sums `cs` of a finished sweep:
+  // E[row][t] = E[t][row] = scale * sum_{j in t} cs[j] for t in [t_first, S), t != row.
+  // Small subunits: one lane sums one subunit (32 subunits per pass, no shuffles);
+  // large subunits: the warp strides over the subunit and butterfly-reduces.
+  auto regroup = [&](const T* cs, int row, int t_first) {
+    for (int t0 = t_first; t0 < S; t0 += 32) {
+      const int t = t0 + lane;
+      const bool mine = t < S && t != row;
+      const int j0 = mine ? suoff[t] : 0;
+      const int len = mine ? suoff[t + 1] - j0 : 0;
+      const bool small = len <= REGROUP_SMALL;
+      const int span = small ? len : 0;
+      const int longest_span = __reduce_max_sync(0xffffffffu, span);
+      double v0 = 0.0, v1 = 0.0;
+      for (int k = 0; k < longest_span; k += 2) {
+        if (k < span) v0 += (double)cs[j0 + k];
+        if (k + 1 < span) v1 += (double)cs[j0 + k + 1];
+      }
+      if (mine && small) { const double v = (v0 + v1) * scale; E[row * S + t] = v; E[t * S + row] = v; }
+      unsigned big = __ballot_sync(0xffffffffu, mine && !small);
+      while (big) {
+        const int tb = t0 + (__ffs(big) - 1);
+        big &= big - 1;
+        double v = 0.0;
+        for (int j = suoff[tb] + lane; j < suoff[tb + 1]; j += 32) v += (double)cs[j];
+        v = warp_sum(v) * scale;
+        if (lane == 0) { E[row * S + tb] = v; E[tb * S + row] = v; }
+      }
+    }
+  };
+  auto refresh_erow = [&]() {  // erow[s] = sum_t E[s][t], one lane per row, fixed order
+    __syncwarp();
+    for (int s = lane; s < S; s += 32) {
+      double v = 0.0;
+      for (int t = 0; t < S; ++t) v += (t == s) ? 0.0 : E[s * S + t];
+      erow[s] = v;
+    }
+    __syncwarp();
+  };
+  // CRITICAL-PATH half of a proposal: the draws of optimizer.py:214-244, the translation
+  // vector, the displaced rows Q and the sweep descriptor.  The other warps are waiting at
+  // barrier A while this runs; everything that is not needed to START the sweep (bond
+  // energies of the trial geometry, energy-table refresh, trace) is done in `deferred`.
+  auto propose = [&](int buf) {
     kb = (int)pcg_bounded(rng, (uint32_t)B);                       // :214
     const int sa = bslot[2 * kb], sb = bslot[2 * kb + 1];
     const double bvx = (double)X[sb] - (double)X[sa];              // :215-217 (P[b1] - P[b0])
@@ -230,14 +304,19 @@ mch_optimize_kernel(const __grid_constant__ OptArgs a) {
     const int side = (int)pcg_bounded(rng, 2u);                    // :225
     ms = bsu[2 * kb + side];
     const double rnd = (pcg_double(rng) - 0.5) * 2.0;              // :229
-    // molecule centroid from the per-subunit sums                 // :236-237
-    double tx = 0.0, ty = 0.0, tz = 0.0;
-    for (int s = lane; s < S; s += 32) { tx += csum[3 * s]; ty += csum[3 * s + 1]; tz += csum[3 * s + 2]; }
-    tx = warp_sum(tx); ty = warp_sum(ty); tz = warp_sum(tz);
-    const double nms = (double)(suoff[ms + 1] - suoff[ms]);
-    const double cvx = csum[3 * ms] / nms - tx / N;
-    const double cvy = csum[3 * ms + 1] / nms - ty / N;
-    const double cvz = csum[3 * ms + 2] / nms - tz / N;
+    // subunit centroid minus molecule centroid                    // :236-237
+    double cvx, cvy, cvz;
+    if (kFast) {
+      const double in = invn[ms], iN = 1.0 / (double)N;
+      cvx = csum[3 * ms] * in - ctot[0] * iN;
+      cvy = csum[3 * ms + 1] * in - ctot[1] * iN;
+      cvz = csum[3 * ms + 2] * in - ctot[2] * iN;
+    } else {
+      const double nms = (double)(suoff[ms + 1] - suoff[ms]);
+      cvx = csum[3 * ms] / nms - ctot[0] / N;
+      cvy = csum[3 * ms + 1] / nms - ctot[1] / N;
+      cvz = csum[3 * ms + 2] / nms - ctot[2] / N;
+    }
     kind = (int)pcg_bounded(rng, 2u);                              // :242-244
     const double ss = a.p.step_size;
     double vx, vy, vz;
@@ -245,11 +324,19 @@ mch_optimize_kernel(const __grid_constant__ OptArgs a) {
     else           { vx = (cvx * ss) * rnd;    vy = (cvy * ss) * rnd;    vz = (cvz * ss) * rnd; }      // :238
     tvx = (T)vx; tvy = (T)vy; tvz = (T)vz;
     const int n = fill_rows(ms, tvx, tvy, tvz);                    // :248-252  (pos - vector)
-    double longest;
-    Ub_trial = bond_terms(ms, tvx, tvy, tvz, longest);
     if (lane == 0) {
       ctl->nrows = n; ctl->c0 = 0; ctl->g0 = suoff[ms]; ctl->g1 = suoff[ms + 1]; ctl->c1 = N; ctl->ms = ms;
+      ctl->buf = buf;
     }
+  };
+  // exp(x) > r for x <= 0, r in [0, 1): decided by a fast fp32 exponential whenever it is
+  // clear of r by more than its own error, by the fp64 exponential otherwise -- the outcome
+  // always equals the fp64 comparison (reference mc_operations.py:49-52).
+  auto boltzmann_beats = [&](double x, double r) {
+    const float ef = __expf((float)x);
+    const float rf = (float)r;
+    if (fabsf(ef - rf) > 2.0e-3f * fmaxf(ef, rf)) return ef > rf;
+    return exp(x) > r;
   };
 
   // ---------------------------------------------------------------- step 0: full evaluation
@@ -258,47 +345,46 @@ mch_optimize_kernel(const __grid_constant__ OptArgs a) {
   for (int s = 0; s < S; ++s) {
     if (warp == 0) {
       const int n = fill_rows(s, (T)0, (T)0, (T)0);
-      if (lane == 0) { ctl->nrows = n; ctl->c0 = suoff[s + 1]; ctl->g0 = suoff[s + 1]; ctl->g1 = suoff[s + 1]; ctl->c1 = N; ctl->ms = s; }
+      if (lane == 0) { ctl->nrows = n; ctl->c0 = suoff[s + 1]; ctl->g0 = suoff[s + 1]; ctl->g1 = suoff[s + 1]; ctl->c1 = N; ctl->ms = s; ctl->buf = 0; }
     }
     __syncthreads();
     {
-      const int nrows = ctl->nrows;
       Cols cross{ctl->c0, ctl->g0, ctl->g1, ctl->c1};
-      double part = pair_sweep<T, MUK, false>(Q, nrows, X, Y, Z, colsum, cross, term);
-      part = warp_sum(part);
-      const int r0 = suoff[s];
+      (void)pair_sweep<T, MUK, false, true>(Q, ctl->nrows, X, Y, Z, colsum, cross, term);
+      const int r0 = suoff[s], nrows = suoff[s + 1] - r0;
       Cols own{r0, r0 + nrows, r0 + nrows, r0 + nrows};
-      double tri = pair_sweep<T, MUK, true>(Q, nrows, X, Y, Z, (T*)nullptr, own, term);
+      double tri = pair_sweep<T, MUK, true, false>(Q, nrows, X, Y, Z, (T*)nullptr, own, term);
       tri = warp_sum(tri);
-      if (lane == 0) { wsum[warp] = part; wsum[32 + warp] = tri; }
+      if (lane == 0) wsum[32 + warp] = tri;
     }
     __syncthreads();
     if (warp == 0) {
       for (int w = 0; w < nwarps; ++w) e_intra += wsum[32 + w];
-      for (int t = s + 1; t < S; ++t) {
-        double v = 0.0;
-        for (int j = suoff[t] + lane; j < suoff[t + 1]; j += 32) v += (double)colsum[j];
-        v = warp_sum(v) * scale;
-        if (lane == 0) { E[s * S + t] = v; E[t * S + s] = v; }
-      }
-      const unsigned long long n = (unsigned long long)ctl->nrows;
+      regroup(colsum, s, s + 1);
+      const unsigned long long n = (unsigned long long)(suoff[s + 1] - suoff[s]);
       pair_count += n * (unsigned long long)(N - suoff[s + 1]) + n * (n - 1ULL) / 2ULL;
     }
   }
+  // deferred bookkeeping of the step whose decision was just taken (warp 0 registers)
+  bool d_accepted = false;  // its move was accepted: row/column d_ms of E is stale
+  int d_ms = 0, d_buf = 0, d_step = 0;
   if (warp == 0) {
     __syncwarp();
     e_intra *= scale;
     double cross = 0.0;
     for (int k = lane; k < S * S; k += 32) { const int s = k / S, t = k - s * S; if (t > s) cross += E[k]; }
     Unb = warp_sum(cross) + e_intra;
+    refresh_erow();
     for (int s = 0; s < S; ++s) refresh_csum(s);
+    __syncwarp();
+    refresh_ctot();
     double longest;
     U = Unb + bond_terms(-1, (T)0, (T)0, (T)0, longest);
     info = -1;
     write_trace(0, longest);
     if (a.num_steps <= 1 && lane == 0) a.maxd[c] = longest;
     __syncwarp();
-    if (a.num_steps > 1) propose();
+    if (a.num_steps > 1) propose(1);
   }
 
   // ---------------------------------------------------------------- Monte-Carlo steps
@@ -313,9 +399,27 @@ mch_optimize_kernel(const __grid_constant__ OptArgs a) {
         store_io<Tio>(a.traj, dst + 2, (double)Z[n] + origin[2]);
       }
     }
+    if (warp == 0) {
+      // DEFERRED half of the control work, overlapped with the other warps' sweep:
+      // (1) the previous move was accepted -> rebuild row/column d_ms of the energy table
+      //     from the column sums of the PREVIOUS sweep (the other buffer),
+      // (2) trace record of the previous step, (3) bond energy of the trial geometry.
+      if (d_accepted) {
+        regroup(colsum + d_buf * colsum_stride, d_ms, 0);
+        refresh_erow();
+        d_accepted = false;
+      }
+      if (d_step > 0 && (a.trace_f || a.trace_i)) {
+        double longest = 0.0;
+        if (a.trace_f) (void)bond_terms(-1, (T)0, (T)0, (T)0, longest);
+        write_trace(d_step, longest);
+      }
+      double unused;
+      Ub_trial = bond_terms(ms, tvx, tvy, tvz, unused);
+    }
     {
       Cols others{ctl->c0, ctl->g0, ctl->g1, ctl->c1};
-      double part = pair_sweep<T, MUK, false>(Q, ctl->nrows, X, Y, Z, colsum, others, term);
+      double part = pair_sweep<T, MUK, false, true>(Q, ctl->nrows, X, Y, Z, colsum + ctl->buf * colsum_stride, others, term);
       part = warp_sum(part);
       if (lane == 0) wsum[warp] = part;
     }
@@ -324,28 +428,29 @@ mch_optimize_kernel(const __grid_constant__ OptArgs a) {
       double fresh = 0.0;
       for (int w = 0; w < nwarps; ++w) fresh += wsum[w];
       fresh *= scale;
-      double old = 0.0;
-      for (int t = lane; t < S; t += 32) old += (t == ms) ? 0.0 : E[ms * S + t];
-      old = warp_sum(old);
-      const double Unb_new = Unb + (fresh - old);
+      const double Unb_new = Unb + (fresh - erow[ms]);
       const double U_new = Unb_new + Ub_trial;
       bool ok;
-      if (U_new < U) ok = true;                                           // mc_operations.py:46-47
-      else ok = exp(-a.p.beta * (U_new - U)) > pcg_double(rng);           // mc_operations.py:49-52
+      if (U_new < U) ok = true;                                                       // mc_operations.py:46-47
+      else ok = boltzmann_beats(-a.p.beta * (U_new - U), pcg_double(rng));            // mc_operations.py:49-52
       const int r0 = suoff[ms], n = suoff[ms + 1] - r0;
       pair_count += (unsigned long long)n * (unsigned long long)(N - n);
       if (ok) {
         for (int i = lane; i < n; i += 32) { const Row4<T> q = Q[i]; X[r0 + i] = q.x; Y[r0 + i] = q.y; Z[r0 + i] = q.z; }
-        for (int t = 0; t < S; ++t) {
-          if (t == ms) continue;
-          double v = 0.0;
-          for (int j = suoff[t] + lane; j < suoff[t + 1]; j += 32) v += (double)colsum[j];
-          v = warp_sum(v) * scale;
-          if (lane == 0) { E[ms * S + t] = v; E[t * S + ms] = v; }
-        }
         U = U_new; Unb = Unb_new; ++n_acc;
         __syncwarp();
-        refresh_csum(ms);
+        if (kFast) {
+          // rigid translation: every sum moves by n * tv (no re-summation of the subunit)
+          if (lane < 3) {
+            const double d = (double)n * (double)(lane == 0 ? tvx : (lane == 1 ? tvy : tvz));
+            csum[3 * ms + lane] -= d;
+            ctot[lane] -= d;
+          }
+        } else {
+          refresh_csum(ms);
+          __syncwarp();
+          refresh_ctot();
+        }
       } else if (a.inexact_undo) {
         // reference optimizer.py:273-277: translate the moved atoms by -tv again
         for (int i = lane; i < n; i += 32) {
@@ -354,20 +459,20 @@ mch_optimize_kernel(const __grid_constant__ OptArgs a) {
         }
         __syncwarp();
         refresh_csum(ms);
+        __syncwarp();
+        refresh_ctot();
       }
       __syncwarp();
       info = kb | ((ok ? 1 : 0) << 16) | (kind << 17) | (ms << 18);
-      const bool last = (step + 1 == a.num_steps);
-      if (a.trace_f || last) {
-        double longest;
-        (void)bond_terms(-1, (T)0, (T)0, (T)0, longest);
-        write_trace(step, longest);
-        if (last && lane == 0) a.maxd[c] = longest;
-      } else {
-        write_trace(step, 0.0);
-      }
-      if (!last) propose();
+      d_accepted = ok; d_ms = ms; d_buf = step & 1; d_step = step;
+      if (step + 1 < a.num_steps) propose((step + 1) & 1);
     }
+  }
+  if (warp == 0 && a.num_steps > 1) {  // the last step has no following sweep to hide behind
+    double longest;
+    (void)bond_terms(-1, (T)0, (T)0, (T)0, longest);
+    write_trace(a.num_steps - 1, longest);
+    if (lane == 0) a.maxd[c] = longest;
   }
   __syncthreads();
 

@@ -1,0 +1,9 @@
+// fp64-compute instantiations of the resident Metropolis kernel (parity mode).
+#include "mch_host.h"
+
+namespace mch {
+int launch_optimize_f64(bool io_f64, int mk, const OptArgs& a, int threads, int smem, cudaStream_t s) {
+  return io_f64 ? launch_optimize_io<double, double>(mk, a, threads, smem, s)
+                : launch_optimize_io<double, float>(mk, a, threads, smem, s);
+}
+}  // namespace mch

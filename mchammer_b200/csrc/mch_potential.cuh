@@ -37,7 +37,7 @@ MCH_HD PotLayout pot_layout(int N, int tsize) {
   L.y = o; o += np * tsize;
   L.z = o; o += np * tsize;
   o = align_up(o, 32);
-  L.rows = o; o += POT_ROWB * 4 * tsize;
+  L.rows = o; o += (POT_ROWB + 4) * 4 * tsize;  // + far-away padding row + prefetch overrun
   L.wsum = o; o += 3 * 32 * 8;
   L.total = align_up(o, 16);
   return L;
@@ -89,16 +89,20 @@ mch_potential_kernel(const __grid_constant__ PotArgs a) {
   double mine = 0.0;
   for (int r0 = 0; r0 < N; r0 += POT_ROWB) {
     const int nrows = (N - r0) < POT_ROWB ? (N - r0) : POT_ROWB;
-    for (int i = tid; i < nrows; i += nt) {
-      Row4<T> q; q.x = X[r0 + i]; q.y = Y[r0 + i]; q.z = Z[r0 + i]; q.w = (T)0;
+    const int nrows_padded = padded_rows(nrows);
+    for (int i = tid; i < nrows_padded; i += nt) {
+      Row4<T> q;
+      if (i < nrows) { q.x = X[r0 + i]; q.y = Y[r0 + i]; q.z = Z[r0 + i]; }
+      else { q.x = far_away<T>(); q.y = far_away<T>(); q.z = far_away<T>(); }
+      q.w = (T)0;
       Q[i] = q;
     }
     __syncthreads();
     const int r1 = r0 + nrows;
     Cols later{r1, r1, r1, N};
-    mine += pair_sweep<T, MUK, false>(Q, nrows, X, Y, Z, (T*)nullptr, later, term);
+    mine += pair_sweep<T, MUK, false, false>(Q, nrows_padded, X, Y, Z, (T*)nullptr, later, term);
     Cols own{r0, r1, r1, r1};
-    mine += pair_sweep<T, MUK, true>(Q, nrows, X, Y, Z, (T*)nullptr, own, term);
+    mine += pair_sweep<T, MUK, true, false>(Q, nrows, X, Y, Z, (T*)nullptr, own, term);
     __syncthreads();
   }
   mine = warp_sum(mine);

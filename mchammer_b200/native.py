@@ -11,7 +11,9 @@ import ctypes as C
 import os
 from functools import lru_cache
 
-LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "libmchammer_b200.so")
+# MCHAMMER_B200_LIB selects another build of the same library (kernel tuning experiments).
+LIB_PATH = os.environ.get("MCHAMMER_B200_LIB") or os.path.join(
+    os.path.dirname(os.path.abspath(__file__)), "libmchammer_b200.so")
 
 MCH_OK = 0
 MCH_F64, MCH_F32 = 0, 1
@@ -19,6 +21,7 @@ MCH_F64, MCH_F32 = 0, 1
 EXPORTS = (
     "mch_optimize_batch", "mch_optimize_smem_bytes", "mch_potential_batch",
     "mch_collapse_batch", "mch_pcg64_seed", "mch_pcg64_stream_check", "mch_probe_fma",
+    "mch_probe_sweep",
     "mch_last_error", "mch_version",
 )
 
@@ -104,6 +107,8 @@ def lib() -> C.CDLL:
     handle.mch_pcg64_stream_check.argtypes = [C.c_void_p, C.c_int, C.c_uint32, C.c_void_p, C.c_void_p]
     handle.mch_probe_fma.restype = C.c_int
     handle.mch_probe_fma.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
+    handle.mch_probe_sweep.restype = C.c_int
+    handle.mch_probe_sweep.argtypes = [C.c_int] * 6 + [C.c_void_p, C.c_void_p]
     return handle
 
 

@@ -11,47 +11,15 @@ lowers the inputs, launches, and raises the device records into the reference's
 from __future__ import annotations
 
 import time
-from dataclasses import dataclass
-from typing import Iterable, Sequence
+from typing import Sequence
 
 import numpy as np
 
 from . import engine, native, rngstate
-from .lowering import LoweredTopology, lower_topology
+from .batch import BatchPlan, BatchResult, shard_bounds, unpack_info
+from .lowering import lower_topology
 from .records import MCStepResult, Result
 from .structure import Molecule
-
-
-@dataclass
-class BatchResult:
-    """Outcome of ``C`` independent chains (host arrays)."""
-
-    positions: np.ndarray            # [C,N,3]
-    system_potential: np.ndarray     # [C]
-    nonbonded_potential: np.ndarray  # [C]
-    max_bond_distance: np.ndarray    # [C]
-    n_accepted: np.ndarray           # [C] accepted moves
-    last_passed: np.ndarray          # [C] 1/0; -1 when no move was made
-    last_bond_index: np.ndarray      # [C] index into bond_pair_ids; -1 when no move
-    pair_evals: np.ndarray           # [C] pair terms the kernel evaluated
-    num_steps: int
-    seconds: float                   # wall time of the call (H2D + kernel + D2H)
-
-    def __len__(self) -> int:
-        return int(self.positions.shape[0])
-
-    def molecule(self, index: int, template: Molecule) -> Molecule:
-        return template.with_position_matrix(np.array(self.positions[index], dtype=np.float64))
-
-
-def _unpack_info(info: np.ndarray):
-    info = np.asarray(info, dtype=np.int64)
-    none = info < 0
-    bond = np.where(none, -1, info & 0xFFFF)
-    passed = np.where(none, -1, (info >> 16) & 1)
-    kind = np.where(none, -1, (info >> 17) & 1)
-    moved = np.where(none, -1, (info >> 18) & 0x1FFF)
-    return bond, passed, kind, moved
 
 
 class Optimizer:
@@ -197,7 +165,7 @@ class Optimizer:
         u = float(out.system_potential.item())
         unb = float(out.nonbonded_potential.item())
         far = float(out.max_bond_distance.item())
-        bond, passed, _, _ = _unpack_info(out.last_step_info.cpu().numpy())
+        bond, passed, _, _ = unpack_info(out.last_step_info.cpu().numpy())
         last_step = max(int(self._num_steps), 1) - 1
         if passed[0] < 0:
             flag, row = None, None
@@ -225,7 +193,7 @@ class Optimizer:
 
         topo, out = self._run_single(mol, bond_pair_ids, subunits, want_trace=True)
         trace = out.trace_potentials[0].cpu().numpy()
-        bond, passed, _, _ = _unpack_info(out.trace_info[0].cpu().numpy())
+        bond, passed, _, _ = unpack_info(out.trace_info[0].cpu().numpy())
         frames = out.trajectory[0].cpu().numpy().astype(np.float64)
         bond_table = np.asarray(bond_pair_ids)
         for step in range(trace.shape[0]):
@@ -253,6 +221,34 @@ class Optimizer:
         return mol.with_position_matrix(final), result
 
     # ------------------------------------------------------------------ many chains
+    def prepare_batch(
+        self,
+        mol: Molecule,
+        bond_pair_ids,
+        subunits: dict,
+        n_chains: int,
+        devices: Sequence[int] | None = None,
+        io_dtype=np.float64,
+        per_chain_positions: bool = False,
+        threads_per_chain: int = 0,
+    ) -> BatchPlan:
+        """Lower the topology once and allocate pinned/device buffers for ``n_chains`` chains.
+
+        ``plan.run(seeds=..., positions=...)`` then costs one H2D copy, one kernel launch per
+        device and one D2H copy.  See :class:`mchammer_b200.batch.BatchPlan`.
+        """
+        native.require_cuda()
+        topo = lower_topology(
+            mol.get_num_atoms(), bond_pair_ids, subunits,
+            require_bond_subunits=self._num_steps > 1,
+        )
+        if devices is None:
+            devices = [self._torch_device().index]
+        return BatchPlan(
+            topo, mol.get_position_matrix(), self._params(), self._num_steps, self._precision,
+            n_chains, list(devices), io_dtype, per_chain_positions, threads_per_chain,
+        )
+
     def get_results_batch(
         self,
         mol: Molecule,
@@ -269,13 +265,12 @@ class Optimizer:
 
         Chain ``c`` is what ``Optimizer(..., random_seed=seeds[c]).get_result(...)`` would
         do to molecule ``c``: ``positions[c]`` if ``positions`` ([C,N,3]) is given, else
-        ``mol`` itself for every chain.  ``seeds`` defaults to ``random_seed + c`` drawn from
-        this optimizer's generator.  Chains are split contiguously over ``devices`` (default:
-        this optimizer's device); there is no inter-device communication -- results are
-        concatenated on the host.
+        ``mol`` itself for every chain.  ``seeds`` default to consecutive integers starting
+        at a value drawn from this optimizer's generator.  Chains are split contiguously
+        over ``devices`` (default: this optimizer's device); there is no inter-device
+        communication -- results are concatenated on the host.
         """
-        torch = native.require_cuda()
-        start = time.perf_counter()
+        native.require_cuda()
         if positions is not None:
             positions = np.ascontiguousarray(positions, dtype=io_dtype)
             if positions.ndim != 3 or positions.shape[1:] != (mol.get_num_atoms(), 3):
@@ -293,61 +288,8 @@ class Optimizer:
             seeds = [base + c for c in range(n_chains)]
         if len(seeds) != n_chains or (positions is not None and positions.shape[0] != n_chains):
             raise ValueError("seeds / positions / n_chains disagree on the number of chains")
-
-        topo = lower_topology(
-            mol.get_num_atoms(), bond_pair_ids, subunits,
-            require_bond_subunits=self._num_steps > 1,
+        plan = self.prepare_batch(
+            mol, bond_pair_ids, subunits, n_chains, devices, io_dtype,
+            per_chain_positions=positions is not None, threads_per_chain=threads_per_chain,
         )
-        words = rngstate.seed_states(seeds)
-        if devices is None:
-            devices = [self._torch_device().index]
-        shards = shard_bounds(n_chains, len(devices))
-        base_pos = np.ascontiguousarray(mol.get_position_matrix(), dtype=io_dtype)
-
-        pending = []
-        for dev_index, (lo, hi) in zip(devices, shards):
-            if hi == lo:
-                continue
-            with torch.cuda.device(dev_index):
-                dev = torch.device("cuda", dev_index)
-                dtopo = engine.upload_topology(topo, dev_index)
-                if positions is None:
-                    pos_dev = engine.host_to_device(base_pos[None], dev, pin=False)
-                else:
-                    pos_dev = engine.host_to_device(positions[lo:hi], dev)
-                rng_dev = engine.rng_words_to_device(words[lo:hi], dev)
-                out = engine.optimize_on_device(
-                    dtopo, pos_dev, hi - lo, rng_dev, self._params(), self._num_steps,
-                    self._precision, threads_per_chain=threads_per_chain,
-                )
-                pending.append((lo, hi, out))
-
-        n = mol.get_num_atoms()
-        res = BatchResult(
-            positions=np.empty((n_chains, n, 3), dtype=io_dtype),
-            system_potential=np.empty(n_chains), nonbonded_potential=np.empty(n_chains),
-            max_bond_distance=np.empty(n_chains), n_accepted=np.empty(n_chains, dtype=np.int64),
-            last_passed=np.empty(n_chains, dtype=np.int64),
-            last_bond_index=np.empty(n_chains, dtype=np.int64),
-            pair_evals=np.empty(n_chains, dtype=np.int64),
-            num_steps=max(int(self._num_steps), 1), seconds=0.0,
-        )
-        for lo, hi, out in pending:  # .cpu() synchronises with each device in turn
-            res.positions[lo:hi] = out.positions.cpu().numpy()
-            res.system_potential[lo:hi] = out.system_potential.cpu().numpy()
-            res.nonbonded_potential[lo:hi] = out.nonbonded_potential.cpu().numpy()
-            res.max_bond_distance[lo:hi] = out.max_bond_distance.cpu().numpy()
-            res.n_accepted[lo:hi] = out.n_accepted.cpu().numpy()
-            bond, passed, _, _ = _unpack_info(out.last_step_info.cpu().numpy())
-            res.last_passed[lo:hi] = passed
-            res.last_bond_index[lo:hi] = bond
-            res.pair_evals[lo:hi] = out.pair_evals.cpu().numpy()
-        res.seconds = time.perf_counter() - start
-        return res
-
-
-def shard_bounds(n_items: int, n_shards: int) -> list[tuple[int, int]]:
-    """Contiguous, balanced ``[lo, hi)`` ranges: shard ``g`` gets items ``g*n/G .. (g+1)*n/G``."""
-    if n_shards <= 0:
-        raise ValueError("n_shards must be positive")
-    return [((g * n_items) // n_shards, ((g + 1) * n_items) // n_shards) for g in range(n_shards)]
+        return plan.run(seeds=seeds, positions=positions).copy()
