@@ -85,6 +85,7 @@ MCH_HD OptLayout opt_layout(int N, int S, int B, int max_su, int tsize) {
   L.suoff = o; o += align_up(S + 1, 4) * 4;
   L.bslot = o; o += align_up(2 * B, 4) * 4;
   L.bsu = o; o += align_up(2 * B, 4) * 4;
+  o = align_up(o, 8);
   L.ctl = o; o += 64;
   L.total = align_up(o, 16);
   return L;
@@ -94,7 +95,8 @@ struct Ctl {
   int nrows;
   int c0, g0, g1, c1;
   int ms;
-  int buf;  // which column-sum buffer this sweep writes
+  int buf;           // which column-sum buffer this sweep writes
+  double cx, cy, cz; // centre of the expanded row encoding (fp32 mode), else unused
 };
 
 #ifdef __CUDACC__
@@ -193,22 +195,29 @@ mch_optimize_kernel(const __grid_constant__ OptArgs a) {
   // ---------------------------------------------------------------- control-warp state
   // (uniform across the 32 lanes of warp 0; other warps never read it)
   constexpr bool kFast = sizeof(T) == 4;  // fp32 mode: cheaper centroid bookkeeping
+  constexpr bool kXF = kFast && (MCH_XF != 0);  // expanded-form squared distances (mch_device.cuh)
+  constexpr bool kDefer = (MCH_DEFER != 0);
   Pcg64 rng = pcg_load(a.rng + 6LL * c);
   double U = 0.0, Unb = 0.0, Ub_trial = 0.0, e_intra = 0.0;
   T tvx = (T)0, tvy = (T)0, tvz = (T)0;
   int ms = 0, kb = 0, kind = 0, n_acc = 0, info = -1;
   unsigned long long pair_count = 0ULL;
 
-  // Q = P[s] - d, padded with far-away rows to an odd count (see sweep_tile); warp 0 only.
-  // Returns the padded count.
+  // Q = encoded rows of P[s] - d, padded with vanishing rows to an odd count (see sweep_tile);
+  // warp 0 only.  Expanded encoding: relative to the centroid of the displaced subunit, which
+  // is also published for the column side.  Returns the padded count.
   auto fill_rows = [&](int s, T dx, T dy, T dz) {
     const int r0 = suoff[s], n = suoff[s + 1] - r0, np = padded_rows(n);
+    Centre<T> ctr{(T)0, (T)0, (T)0};
+    if (kXF) {
+      ctr.x = (T)(csum[3 * s] * invn[s]) - dx;
+      ctr.y = (T)(csum[3 * s + 1] * invn[s]) - dy;
+      ctr.z = (T)(csum[3 * s + 2] * invn[s]) - dz;
+      if (lane == 0) { ctl->cx = (double)ctr.x; ctl->cy = (double)ctr.y; ctl->cz = (double)ctr.z; }
+    }
     for (int i = lane; i < np; i += 32) {
-      Row4<T> q;
-      if (i < n) { q.x = X[r0 + i] - dx; q.y = Y[r0 + i] - dy; q.z = Z[r0 + i] - dz; }
-      else { q.x = far_away<T>(); q.y = far_away<T>(); q.z = far_away<T>(); }
-      q.w = (T)0;
-      Q[i] = q;
+      Q[i] = i < n ? encode_row<T, kXF>(X[r0 + i] - dx, Y[r0 + i] - dy, Z[r0 + i] - dz, ctr)
+                   : padding_row<T, kXF>();
     }
     return np;
   };
@@ -342,6 +351,12 @@ mch_optimize_kernel(const __grid_constant__ OptArgs a) {
   // ---------------------------------------------------------------- step 0: full evaluation
   // For every subunit s: cross terms against all later subunits (each cross pair once)
   // and the strict lower triangle inside s.
+  if (warp == 0) {
+    for (int s = 0; s < S; ++s) refresh_csum(s);
+    __syncwarp();
+    refresh_ctot();
+    __syncwarp();
+  }
   for (int s = 0; s < S; ++s) {
     if (warp == 0) {
       const int n = fill_rows(s, (T)0, (T)0, (T)0);
@@ -350,10 +365,11 @@ mch_optimize_kernel(const __grid_constant__ OptArgs a) {
     __syncthreads();
     {
       Cols cross{ctl->c0, ctl->g0, ctl->g1, ctl->c1};
-      (void)pair_sweep<T, MUK, false, true>(Q, ctl->nrows, X, Y, Z, colsum, cross, term);
+      const Centre<T> ctr{(T)ctl->cx, (T)ctl->cy, (T)ctl->cz};
+      (void)pair_sweep<T, MUK, false, true, kXF>(Q, ctl->nrows, X, Y, Z, colsum, cross, term, ctr);
       const int r0 = suoff[s], nrows = suoff[s + 1] - r0;
       Cols own{r0, r0 + nrows, r0 + nrows, r0 + nrows};
-      double tri = pair_sweep<T, MUK, true, false>(Q, nrows, X, Y, Z, (T*)nullptr, own, term);
+      double tri = pair_sweep<T, MUK, true, false, kXF>(Q, nrows, X, Y, Z, (T*)nullptr, own, term, ctr);
       tri = warp_sum(tri);
       if (lane == 0) wsum[32 + warp] = tri;
     }
@@ -375,16 +391,16 @@ mch_optimize_kernel(const __grid_constant__ OptArgs a) {
     for (int k = lane; k < S * S; k += 32) { const int s = k / S, t = k - s * S; if (t > s) cross += E[k]; }
     Unb = warp_sum(cross) + e_intra;
     refresh_erow();
-    for (int s = 0; s < S; ++s) refresh_csum(s);
-    __syncwarp();
-    refresh_ctot();
     double longest;
     U = Unb + bond_terms(-1, (T)0, (T)0, (T)0, longest);
     info = -1;
     write_trace(0, longest);
     if (a.num_steps <= 1 && lane == 0) a.maxd[c] = longest;
     __syncwarp();
-    if (a.num_steps > 1) propose(1);
+    if (a.num_steps > 1) {
+      propose(1);
+      if (!kDefer) { double unused; Ub_trial = bond_terms(ms, tvx, tvy, tvz, unused); }
+    }
   }
 
   // ---------------------------------------------------------------- Monte-Carlo steps
@@ -404,22 +420,25 @@ mch_optimize_kernel(const __grid_constant__ OptArgs a) {
       // (1) the previous move was accepted -> rebuild row/column d_ms of the energy table
       //     from the column sums of the PREVIOUS sweep (the other buffer),
       // (2) trace record of the previous step, (3) bond energy of the trial geometry.
-      if (d_accepted) {
-        regroup(colsum + d_buf * colsum_stride, d_ms, 0);
-        refresh_erow();
-        d_accepted = false;
+      if (kDefer) {
+        if (d_accepted) {
+          regroup(colsum + d_buf * colsum_stride, d_ms, 0);
+          refresh_erow();
+          d_accepted = false;
+        }
+        if (d_step > 0 && (a.trace_f || a.trace_i)) {
+          double longest = 0.0;
+          if (a.trace_f) (void)bond_terms(-1, (T)0, (T)0, (T)0, longest);
+          write_trace(d_step, longest);
+        }
+        double unused;
+        Ub_trial = bond_terms(ms, tvx, tvy, tvz, unused);
       }
-      if (d_step > 0 && (a.trace_f || a.trace_i)) {
-        double longest = 0.0;
-        if (a.trace_f) (void)bond_terms(-1, (T)0, (T)0, (T)0, longest);
-        write_trace(d_step, longest);
-      }
-      double unused;
-      Ub_trial = bond_terms(ms, tvx, tvy, tvz, unused);
     }
     {
       Cols others{ctl->c0, ctl->g0, ctl->g1, ctl->c1};
-      double part = pair_sweep<T, MUK, false, true>(Q, ctl->nrows, X, Y, Z, colsum + ctl->buf * colsum_stride, others, term);
+      const Centre<T> ctr{(T)ctl->cx, (T)ctl->cy, (T)ctl->cz};
+      double part = pair_sweep<T, MUK, false, true, kXF>(Q, ctl->nrows, X, Y, Z, colsum + ctl->buf * colsum_stride, others, term, ctr);
       part = warp_sum(part);
       if (lane == 0) wsum[warp] = part;
     }
@@ -436,7 +455,7 @@ mch_optimize_kernel(const __grid_constant__ OptArgs a) {
       const int r0 = suoff[ms], n = suoff[ms + 1] - r0;
       pair_count += (unsigned long long)n * (unsigned long long)(N - n);
       if (ok) {
-        for (int i = lane; i < n; i += 32) { const Row4<T> q = Q[i]; X[r0 + i] = q.x; Y[r0 + i] = q.y; Z[r0 + i] = q.z; }
+        for (int i = lane; i < n; i += 32) { X[r0 + i] -= tvx; Y[r0 + i] -= tvy; Z[r0 + i] -= tvz; }  // = the swept rows
         U = U_new; Unb = Unb_new; ++n_acc;
         __syncwarp();
         if (kFast) {
@@ -454,8 +473,7 @@ mch_optimize_kernel(const __grid_constant__ OptArgs a) {
       } else if (a.inexact_undo) {
         // reference optimizer.py:273-277: translate the moved atoms by -tv again
         for (int i = lane; i < n; i += 32) {
-          const Row4<T> q = Q[i];
-          X[r0 + i] = q.x - (-tvx); Y[r0 + i] = q.y - (-tvy); Z[r0 + i] = q.z - (-tvz);
+          X[r0 + i] = (X[r0 + i] - tvx) - (-tvx); Y[r0 + i] = (Y[r0 + i] - tvy) - (-tvy); Z[r0 + i] = (Z[r0 + i] - tvz) - (-tvz);
         }
         __syncwarp();
         refresh_csum(ms);
@@ -465,7 +483,19 @@ mch_optimize_kernel(const __grid_constant__ OptArgs a) {
       __syncwarp();
       info = kb | ((ok ? 1 : 0) << 16) | (kind << 17) | (ms << 18);
       d_accepted = ok; d_ms = ms; d_buf = step & 1; d_step = step;
-      if (step + 1 < a.num_steps) propose((step + 1) & 1);
+      if (!kDefer) {
+        if (ok) { regroup(colsum + d_buf * colsum_stride, ms, 0); refresh_erow(); }
+        d_accepted = false;
+        if (step + 1 < a.num_steps && (a.trace_f || a.trace_i)) {
+          double longest = 0.0;
+          if (a.trace_f) (void)bond_terms(-1, (T)0, (T)0, (T)0, longest);
+          write_trace(step, longest);
+        }
+      }
+      if (step + 1 < a.num_steps) {
+        propose((step + 1) & 1);
+        if (!kDefer) { double unused; Ub_trial = bond_terms(ms, tvx, tvy, tvz, unused); }
+      }
     }
   }
   if (warp == 0 && a.num_steps > 1) {  // the last step has no following sweep to hide behind

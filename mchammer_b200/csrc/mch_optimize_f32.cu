@@ -24,21 +24,19 @@ probe_sweep_kernel(int iters, int with_barrier, int nrows_real, int ncols, float
   for (int n = threadIdx.x; n < N; n += blockDim.x) {
     X[n] = 0.013f * n + 0.5f * blockIdx.x; Y[n] = 7.0f - 0.009f * n; Z[n] = 0.003f * n * (n & 7);
   }
+  constexpr bool kXF = (MCH_XF != 0);
+  const Centre<float> ctr{-5.7f, 21.7f, -7.8f};
   const int np = padded_rows(nrows_real);
   for (int i = threadIdx.x; i < np + 4; i += blockDim.x) {
-    Row4<float> q;
-    q.x = i < nrows_real ? -3.0f - 0.11f * i : far_away<float>();
-    q.y = i < nrows_real ? 20.0f + 0.07f * i : far_away<float>();
-    q.z = i < nrows_real ? -9.0f + 0.05f * i : far_away<float>();
-    q.w = 0.f;
-    Q[i] = q;
+    Q[i] = i < nrows_real ? encode_row<float, kXF>(-3.0f - 0.11f * i, 20.0f + 0.07f * i, -9.0f + 0.05f * i, ctr)
+                          : padding_row<float, kXF>();
   }
   __syncthreads();
   const PairTerm<float, MU_3> term(3.0, 3);
   double total = 0.0;
   for (int it = 0; it < iters; ++it) {
     Cols cols{0, 0, 50, 50 + ncols};
-    total += pair_sweep<float, MU_3, false, true>(Q, np, X, Y, Z, colsum + (it & 1) * 1008, cols, term);
+    total += pair_sweep<float, MU_3, false, true, kXF>(Q, np, X, Y, Z, colsum + (it & 1) * 1008, cols, term, ctr);
     if (with_barrier) __syncthreads();
   }
   if (total == -1.2345) *sink = (float)total;
