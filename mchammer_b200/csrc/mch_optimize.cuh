@@ -203,7 +203,7 @@ mch_optimize_kernel(const __grid_constant__ OptArgs a) {
   int ms = 0, kb = 0, kind = 0, n_acc = 0, info = -1;
   unsigned long long pair_count = 0ULL;
 
-  // Q = encoded rows of P[s] - d, padded with vanishing rows to an odd count (see sweep_tile);
+  // Q = encoded rows of P[s] - d, padded with vanishing rows to an even count (see sweep_tile);
   // warp 0 only.  Expanded encoding: relative to the centroid of the displaced subunit, which
   // is also published for the column side.  Returns the padded count.
   auto fill_rows = [&](int s, T dx, T dy, T dz) {
@@ -438,7 +438,10 @@ mch_optimize_kernel(const __grid_constant__ OptArgs a) {
     {
       Cols others{ctl->c0, ctl->g0, ctl->g1, ctl->c1};
       const Centre<T> ctr{(T)ctl->cx, (T)ctl->cy, (T)ctl->cz};
-      double part = pair_sweep<T, MUK, false, true, kXF>(Q, ctl->nrows, X, Y, Z, colsum + ctl->buf * colsum_stride, others, term, ctr);
+      // warp 0 spends roughly the time of 100 rows x 32 columns on the deferred control work:
+      // one pair of column units less for subunits of up to ~50 atoms, nothing for large ones
+      const int handicap = kDefer ? min(1, 50 / ctl->nrows) : 0;
+      double part = pair_sweep<T, MUK, false, true, kXF>(Q, ctl->nrows, X, Y, Z, colsum + ctl->buf * colsum_stride, others, term, ctr, handicap);
       part = warp_sum(part);
       if (lane == 0) wsum[warp] = part;
     }
