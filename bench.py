@@ -232,6 +232,16 @@ def measured_peaks():
     return {"hbm_gbs": 6650.0}, "fallback (B200_PROFILING.md)"
 
 
+def profiled_traffic(precision: str):
+    """DRAM bytes per launch of the dominant kernel from the committed `ncu --set full` summary."""
+    name = "r01_ncu_full_fp32.json" if precision == "fp32" else "r01_ncu_full_fp64.json"
+    path = os.path.join(REPO, "profiles", name)
+    if not os.path.exists(path):
+        return None
+    with open(path) as fh:
+        return json.load(fh).get("dram_bytes_per_launch")
+
+
 def probe_pipe_peak(torch, dtype_code: int, device) -> float:
     """TFLOP/s of a pure dependent-FMA kernel (8 chains/thread) -- the arithmetic-pipe roofline."""
     import ctypes as C
@@ -371,7 +381,7 @@ def cuda_arm(args):
                 "bound": "fp32_pipe" if args.precision == "fp32" else "fp64_pipe",
                 "achieved": achieved_tflops, "peak": pipe_peak, "unit": "TFLOP/s",
                 "frac": achieved_tflops / pipe_peak if pipe_peak else None,
-                "traffic": None,
+                "traffic": profiled_traffic(args.precision) if args.workload == "cube1000" and chains == 4096 else None,
                 "kernel": "mch_optimize_kernel",
                 "note": f"achieved = {FLOPS_PER_PAIR:.0f} flops/pair x {pairs_per_launch} pairs per launch / "
                         "CUDA-event launch time; peak = dependent-FMA probe (mch_probe_fma) measured in this run; "

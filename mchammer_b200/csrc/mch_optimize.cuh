@@ -59,6 +59,23 @@ struct OptArgs {
   int inexact_undo;          // 1: reproduce (p - v) + v on reject (fp64 parity)
 };
 
+struct Ctl {
+  int nrows;
+  int c0, g0, g1, c1;
+  int ms;
+  int buf;           // which column-sum buffer this sweep writes
+  double cx, cy, cz; // centre of the expanded row encoding (fp32 mode), else unused
+  double origin[3];  // frame shift of the fp32 mode (start centroid), zero in fp64 mode
+  // Control-warp state parked here while the warp sweeps (the sweep tiles are real function
+  // calls; anything kept in registers across them would be spilled to local memory, which
+  // at 208 KB of shared memory per SM means L2 latency on every reload).
+  unsigned long long rng_hi, rng_lo, rng_inc_hi, rng_inc_lo, pair_count;
+  double U, Unb, Ub_trial;
+  double tv[3];
+  unsigned rng_has32, rng_half;
+  int kb, kind, n_acc, info, d_accepted, d_ms, d_buf, d_step, cur_ms;
+};
+
 // Shared-memory carve-up, identical on host (size query) and device.
 struct OptLayout {
   int x, y, z, colsum, colsum_stride, rows, E, erow, csum, invn, wsum, suoff, bslot, bsu, ctl, total;
@@ -85,19 +102,12 @@ MCH_HD OptLayout opt_layout(int N, int S, int B, int max_su, int tsize) {
   L.suoff = o; o += align_up(S + 1, 4) * 4;
   L.bslot = o; o += align_up(2 * B, 4) * 4;
   L.bsu = o; o += align_up(2 * B, 4) * 4;
-  o = align_up(o, 8);
-  L.ctl = o; o += 64;
+  o = align_up(o, 16);
+  L.ctl = o; o += (int)sizeof(Ctl);
   L.total = align_up(o, 16);
   return L;
 }
 
-struct Ctl {
-  int nrows;
-  int c0, g0, g1, c1;
-  int ms;
-  int buf;           // which column-sum buffer this sweep writes
-  double cx, cy, cz; // centre of the expanded row encoding (fp32 mode), else unused
-};
 
 #ifdef __CUDACC__
 
@@ -113,7 +123,7 @@ template <typename Tio> MCH_D void store_io(void* base, long long idx, double v)
 constexpr int REGROUP_SMALL = 64;
 
 #ifndef MCH_F32_THREADS_PER_SM
-#define MCH_F32_THREADS_PER_SM 1024
+#define MCH_F32_THREADS_PER_SM 768  // 80 registers per thread, 6 chains (24 warps) per SM: measured best
 #endif
 
 // NTMAX: largest block this instantiation may be launched with.  fp32: 1024 / NTMAX blocks
@@ -164,7 +174,7 @@ mch_optimize_kernel(const __grid_constant__ OptArgs a) {
   const long long in_base = (long long)c * a.pos_in_stride;
   // fp32 compute works in a frame centred on the start geometry (translation invariant
   // path; keeps |coordinates| small).  fp64 keeps the caller's frame bit for bit.
-  double origin[3] = {0.0, 0.0, 0.0};
+  double origin[3] = {0.0, 0.0, 0.0};  // prologue only; kept in ctl->origin afterwards
   if (sizeof(T) == 4) {
     double sx = 0.0, sy = 0.0, sz = 0.0;
     for (int n = tid; n < N; n += nt) {
@@ -188,6 +198,7 @@ mch_optimize_kernel(const __grid_constant__ OptArgs a) {
     Y[n] = (T)(load_io<Tio>(a.pos_in, src + 1) - origin[1]);
     Z[n] = (T)(load_io<Tio>(a.pos_in, src + 2) - origin[2]);
   }
+  if (tid == 0) { ctl->origin[0] = origin[0]; ctl->origin[1] = origin[1]; ctl->origin[2] = origin[2]; }
   for (int k = tid; k < S * S; k += nt) E[k] = 0.0;
   for (int k = tid; k < S; k += nt) invn[k] = 1.0 / (double)(suoff[k + 1] - suoff[k]);
   __syncthreads();
@@ -197,12 +208,34 @@ mch_optimize_kernel(const __grid_constant__ OptArgs a) {
   constexpr bool kFast = sizeof(T) == 4;  // fp32 mode: cheaper centroid bookkeeping
   constexpr bool kXF = kFast && (MCH_XF != 0);  // expanded-form squared distances (mch_device.cuh)
   constexpr bool kDefer = (MCH_DEFER != 0);
-  Pcg64 rng = pcg_load(a.rng + 6LL * c);
-  double U = 0.0, Unb = 0.0, Ub_trial = 0.0, e_intra = 0.0;
+  Pcg64 rng;  // loaded after step 0 (nothing of the control state is live across the step-0 sweeps)
+  rng.hi = rng.lo = rng.inc_hi = rng.inc_lo = 0ULL; rng.has32 = rng.half = 0u;
+  double U = 0.0, Unb = 0.0, Ub_trial = 0.0;
   T tvx = (T)0, tvy = (T)0, tvz = (T)0;
   int ms = 0, kb = 0, kind = 0, n_acc = 0, info = -1;
   unsigned long long pair_count = 0ULL;
 
+  bool d_accepted = false;  // the last decided move was accepted: row/column d_ms of E is stale
+  int d_ms = 0, d_buf = 0, d_step = 0;
+  auto park = [&]() {  // registers -> shared memory (lane 0 writes; every lane holds the same values)
+    if (lane == 0) {
+      ctl->rng_hi = rng.hi; ctl->rng_lo = rng.lo; ctl->rng_inc_hi = rng.inc_hi; ctl->rng_inc_lo = rng.inc_lo;
+      ctl->rng_has32 = rng.has32; ctl->rng_half = rng.half;
+      ctl->U = U; ctl->Unb = Unb; ctl->Ub_trial = Ub_trial; ctl->pair_count = pair_count;
+      ctl->tv[0] = (double)tvx; ctl->tv[1] = (double)tvy; ctl->tv[2] = (double)tvz;
+      ctl->kb = kb; ctl->kind = kind; ctl->n_acc = n_acc; ctl->info = info; ctl->cur_ms = ms;
+      ctl->d_accepted = d_accepted ? 1 : 0; ctl->d_ms = d_ms; ctl->d_buf = d_buf; ctl->d_step = d_step;
+    }
+    __syncwarp();
+  };
+  auto unpark = [&]() {  // shared memory -> registers of all 32 lanes
+    rng.hi = ctl->rng_hi; rng.lo = ctl->rng_lo; rng.inc_hi = ctl->rng_inc_hi; rng.inc_lo = ctl->rng_inc_lo;
+    rng.has32 = ctl->rng_has32; rng.half = ctl->rng_half;
+    U = ctl->U; Unb = ctl->Unb; Ub_trial = ctl->Ub_trial; pair_count = ctl->pair_count;
+    tvx = (T)ctl->tv[0]; tvy = (T)ctl->tv[1]; tvz = (T)ctl->tv[2];
+    kb = ctl->kb; kind = ctl->kind; n_acc = ctl->n_acc; info = ctl->info; ms = ctl->cur_ms;
+    d_accepted = ctl->d_accepted != 0; d_ms = ctl->d_ms; d_buf = ctl->d_buf; d_step = ctl->d_step;
+  };
   // Q = encoded rows of P[s] - d, padded with vanishing rows to an even count (see sweep_tile);
   // warp 0 only.  Expanded encoding: relative to the centroid of the displaced subunit, which
   // is also published for the column side.  Returns the padded count.
@@ -355,6 +388,7 @@ mch_optimize_kernel(const __grid_constant__ OptArgs a) {
     for (int s = 0; s < S; ++s) refresh_csum(s);
     __syncwarp();
     refresh_ctot();
+    if (lane == 0) ctl->U = 0.0;  // accumulates the intra-subunit sum during step 0
     __syncwarp();
   }
   for (int s = 0; s < S; ++s) {
@@ -375,18 +409,17 @@ mch_optimize_kernel(const __grid_constant__ OptArgs a) {
     }
     __syncthreads();
     if (warp == 0) {
-      for (int w = 0; w < nwarps; ++w) e_intra += wsum[32 + w];
+      double intra = 0.0;
+      for (int w = 0; w < nwarps; ++w) intra += wsum[32 + w];
+      if (lane == 0) ctl->U += intra;
       regroup(colsum, s, s + 1);
-      const unsigned long long n = (unsigned long long)(suoff[s + 1] - suoff[s]);
-      pair_count += n * (unsigned long long)(N - suoff[s + 1]) + n * (n - 1ULL) / 2ULL;
     }
   }
-  // deferred bookkeeping of the step whose decision was just taken (warp 0 registers)
-  bool d_accepted = false;  // its move was accepted: row/column d_ms of E is stale
-  int d_ms = 0, d_buf = 0, d_step = 0;
   if (warp == 0) {
     __syncwarp();
-    e_intra *= scale;
+    rng = pcg_load(a.rng + 6LL * c);
+    pair_count = (unsigned long long)N * (unsigned long long)(N - 1) / 2ULL;  // step 0: every pair once
+    const double e_intra = ctl->U * scale;
     double cross = 0.0;
     for (int k = lane; k < S * S; k += 32) { const int s = k / S, t = k - s * S; if (t > s) cross += E[k]; }
     Unb = warp_sum(cross) + e_intra;
@@ -410,9 +443,9 @@ mch_optimize_kernel(const __grid_constant__ OptArgs a) {
       const long long frame = ((long long)c * a.num_steps + (step - 1)) * N * 3;
       for (int n = tid; n < N; n += nt) {
         const long long dst = frame + 3LL * a.perm[n];
-        store_io<Tio>(a.traj, dst + 0, (double)X[n] + origin[0]);
-        store_io<Tio>(a.traj, dst + 1, (double)Y[n] + origin[1]);
-        store_io<Tio>(a.traj, dst + 2, (double)Z[n] + origin[2]);
+        store_io<Tio>(a.traj, dst + 0, (double)X[n] + ctl->origin[0]);
+        store_io<Tio>(a.traj, dst + 1, (double)Y[n] + ctl->origin[1]);
+        store_io<Tio>(a.traj, dst + 2, (double)Z[n] + ctl->origin[2]);
       }
     }
     if (warp == 0) {
@@ -434,6 +467,7 @@ mch_optimize_kernel(const __grid_constant__ OptArgs a) {
         double unused;
         Ub_trial = bond_terms(ms, tvx, tvy, tvz, unused);
       }
+      park();
     }
     {
       Cols others{ctl->c0, ctl->g0, ctl->g1, ctl->c1};
@@ -447,6 +481,7 @@ mch_optimize_kernel(const __grid_constant__ OptArgs a) {
     }
     __syncthreads();  // B: column sums and warp totals published
     if (warp == 0) {
+      unpark();
       double fresh = 0.0;
       for (int w = 0; w < nwarps; ++w) fresh += wsum[w];
       fresh *= scale;
@@ -512,7 +547,7 @@ mch_optimize_kernel(const __grid_constant__ OptArgs a) {
   // ---------------------------------------------------------------- epilogue
   for (int n = tid; n < N; n += nt) {
     const long long at = 3LL * a.perm[n];
-    const double px = (double)X[n] + origin[0], py = (double)Y[n] + origin[1], pz = (double)Z[n] + origin[2];
+    const double px = (double)X[n] + ctl->origin[0], py = (double)Y[n] + ctl->origin[1], pz = (double)Z[n] + ctl->origin[2];
     const long long dst = (long long)c * N * 3 + at;
     store_io<Tio>(a.pos_out, dst + 0, px); store_io<Tio>(a.pos_out, dst + 1, py); store_io<Tio>(a.pos_out, dst + 2, pz);
     if (a.traj) {

@@ -1,10 +1,14 @@
 """Summarise an .ncu-rep (raw + source pages) into the few numbers DESIGN.md quotes.
 
-    python profiles/ncu_summary.py gpurun_out/prof.ncu-rep [kernel-regex]
+    python profiles/ncu_summary.py gpurun_out/prof.ncu-rep [--json profiles/rNN_ncu_full.json]
+
+The JSON (per-launch DRAM bytes, duration, occupancy, pipe utilisation) is what bench.py reads
+for `roofline.traffic`.
 """
 import collections
 import csv
 import io
+import json
 import subprocess
 import sys
 
@@ -35,11 +39,31 @@ def main():
     rep = sys.argv[1]
     raw = page(rep, "raw")
     hdr, units = raw[0], raw[1]
+    summary = {}
     for row in raw[2:]:
         print("kernel:", row[hdr.index("Kernel Name")][:90])
+        summary = {"kernel": row[hdr.index("Kernel Name")]}
         for k in KEYS:
             if k in hdr:
                 print(f"  {k:68s} {row[hdr.index(k)]:>16s} {units[hdr.index(k)]}")
+                try:
+                    summary[k] = {"value": float(row[hdr.index(k)].replace(",", "")), "unit": units[hdr.index(k)]}
+                except ValueError:
+                    pass
+
+    def to_bytes(key):
+        item = summary.get(key)
+        if not item:
+            return None
+        scale = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}.get(item["unit"], 1)
+        return item["value"] * scale
+
+    rd, wr = to_bytes("dram__bytes_read.sum"), to_bytes("dram__bytes_write.sum")
+    if rd is not None and wr is not None:
+        summary["dram_bytes_per_launch"] = rd + wr
+    if "--json" in sys.argv:
+        with open(sys.argv[sys.argv.index("--json") + 1], "w") as fh:
+            json.dump(summary, fh, indent=1)
     src = page(rep, "source")
     hdr = next(r for r in src if r and r[0] == "Address")
     rows = src[src.index(hdr) + 1:]

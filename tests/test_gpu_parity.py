@@ -277,6 +277,25 @@ def test_fp32_mode_tolerance_against_reference():
         assert rel_close(unb, g["nonbonded_potential"][:prefix], RTOL32)
 
 
+def test_fp32_expanded_form_energy_accuracy():
+    # fp32 fast mode forms r^2 in the expanded form around the moving subunit's centroid
+    # (csrc/mch_device.cuh); step 0 of the step kernel sums every pair that way.  Stated
+    # tolerance 1e-4 relative; required here: 1e-5, also far from the origin and on the
+    # 5004-atom cage (radius ~45 A).
+    exact = mch.Optimizer(0.25, 1.2, 1, precision="fp64")
+    fast = mch.Optimizer(0.25, 1.2, 1, precision="fp32")
+    cases = [synthetic.cube_cage(), synthetic.cuboctahedron_cage()]
+    mol, lb, su = cases[0]
+    cases.append((mol.with_displacement(np.array([1234.5, -987.25, 4321.0])), lb, su))
+    for mol, long_bonds, subunits in cases:
+        want_u, want_unb = exact.compute_potential(mol, long_bonds)
+        got = fast.get_results_batch(mol, long_bonds, subunits, seeds=[1])
+        assert np.isclose(got.nonbonded_potential[0], want_unb, rtol=1e-5, atol=0)
+        assert np.isclose(got.system_potential[0], want_u, rtol=1e-5, atol=0)
+        ref64 = exact.get_results_batch(mol, long_bonds, subunits, seeds=[1])
+        assert np.isclose(ref64.nonbonded_potential[0], want_unb, rtol=1e-12, atol=0)
+
+
 # ------------------------------------------------------------------------- properties at BASELINE size
 @pytest.mark.parametrize("precision,rtol,atol", [("fp64", 1e-9, 1e-9), ("fp32", 1e-4, 2e-4)])
 def test_full_size_cage_properties(precision, rtol, atol):
