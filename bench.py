@@ -325,6 +325,7 @@ def cuda_arm(args):
     kernel_ms = [a.elapsed_time(b) for a, b in events]
     dev_seconds = sum(kernel_ms) * 1e-3
     pairs_per_launch = int(plan.shards[0].out.pair_evals.sum().item())
+    gpu_launches_e2e = len(plan._slices(chains))
 
     # ---------------- end to end through the public API (host buffers in, host buffers out)
     host_positions = plan.h_pos_in  # pinned [C,N,3]; per-chain start geometries
@@ -391,8 +392,10 @@ def cuda_arm(args):
                         "peak_source": peaks_src},
             },
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "api": "Optimizer.prepare_batch(...).run(rng_words, positions) with pinned host buffers"},
+                    "api": "Optimizer.prepare_batch(...).run(rng_words, positions) with pinned host buffers; "
+                           "the call pipelines H2D / kernel / D2H over 4 slices of the batch"},
             "gpu_launches": args.steps,
+            "gpu_launches_e2e": args.steps * gpu_launches_e2e,
             "clocks": clocks,
         }
         if world == 1 and not args.no_cpu_baseline:

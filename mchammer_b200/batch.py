@@ -78,7 +78,28 @@ class _Shard:
             rows = self.count if per_chain_positions else 1
             self.pos_in = torch.empty((rows, n, 3), dtype=io_torch_dtype, device=self.device)
             self.rng = torch.empty((self.count, 6), dtype=torch.int64, device=self.device)
-            self.out = None  # engine.OptimizeOutput, allocated by the first launch and reused
+            f64 = dict(dtype=torch.float64, device=self.device)
+            i32 = dict(dtype=torch.int32, device=self.device)
+            self.out = engine.OptimizeOutput(
+                positions=torch.empty((self.count, n, 3), dtype=io_torch_dtype, device=self.device),
+                system_potential=torch.empty(self.count, **f64),
+                nonbonded_potential=torch.empty(self.count, **f64),
+                max_bond_distance=torch.empty(self.count, **f64),
+                n_accepted=torch.empty(self.count, **i32), last_step_info=torch.empty(self.count, **i32),
+                rng_state=self.rng, pair_evals=torch.empty(self.count, dtype=torch.int64, device=self.device),
+                trace_potentials=None, trace_info=None, trajectory=None,
+            )
+            self.streams = []  # side streams of the pipelined run, created on first use
+
+    def out_slice(self, lo: int, hi: int) -> "engine.OptimizeOutput":
+        o = self.out
+        return engine.OptimizeOutput(
+            positions=o.positions[lo:hi], system_potential=o.system_potential[lo:hi],
+            nonbonded_potential=o.nonbonded_potential[lo:hi], max_bond_distance=o.max_bond_distance[lo:hi],
+            n_accepted=o.n_accepted[lo:hi], last_step_info=o.last_step_info[lo:hi],
+            rng_state=self.rng[lo:hi], pair_evals=o.pair_evals[lo:hi],
+            trace_potentials=None, trace_info=None, trajectory=None,
+        )
 
 
 class BatchPlan:
@@ -90,7 +111,7 @@ class BatchPlan:
 
     def __init__(self, topo: LoweredTopology, base_positions: np.ndarray, params, num_steps: int,
                  precision: str, n_chains: int, devices: Sequence[int], io_dtype=np.float64,
-                 per_chain_positions: bool = False, threads_per_chain: int = 0):
+                 per_chain_positions: bool = False, threads_per_chain: int = 0, n_slices: int = 0):
         torch = native.require_cuda()
         native.lib()
         self._torch = torch
@@ -101,6 +122,9 @@ class BatchPlan:
         self.n_chains = int(n_chains)
         self.threads_per_chain = int(threads_per_chain)
         self.per_chain_positions = bool(per_chain_positions)
+        # `run` cuts every device's chains into slices and pipelines H2D / kernel / D2H of
+        # consecutive slices on side streams (0 = choose: 4 slices once the batch is large)
+        self.n_slices = int(n_slices)
         self.io_dtype = np.dtype(io_dtype)
         if self.io_dtype not in (np.dtype(np.float64), np.dtype(np.float32)):
             raise TypeError("io_dtype must be float64 or float32")
@@ -197,12 +221,56 @@ class BatchPlan:
             num_steps=self.num_steps, seconds=seconds, h2d_bytes=h2d, d2h_bytes=d2h,
         )
 
+    def _slices(self, count: int) -> list[tuple[int, int]]:
+        n = self.n_slices if self.n_slices > 0 else (4 if count >= 2048 else 1)
+        n = max(1, min(n, count))
+        return [b for b in shard_bounds(count, n) if b[1] > b[0]]
+
+    def _run_pipelined(self) -> int:
+        """H2D -> kernel -> D2H per slice on side streams, so the copies of one slice overlap
+        the kernel of another.  Returns the bytes read back."""
+        torch = self._torch
+        for sh in self.shards:
+            with torch.cuda.device(sh.device):
+                main = torch.cuda.current_stream(sh.device)
+                slices = self._slices(sh.count)
+                while len(sh.streams) < min(3, len(slices)):
+                    sh.streams.append(torch.cuda.Stream(device=sh.device))
+                if not self.per_chain_positions:
+                    sh.pos_in.copy_(self.h_pos_in, non_blocking=True)
+                for st in sh.streams:
+                    st.wait_stream(main)
+                for k, (lo, hi) in enumerate(slices):
+                    with torch.cuda.stream(sh.streams[k % len(sh.streams)]):
+                        g_lo, g_hi = sh.lo + lo, sh.lo + hi
+                        if self.per_chain_positions:
+                            sh.pos_in[lo:hi].copy_(self.h_pos_in[g_lo:g_hi], non_blocking=True)
+                            pos = sh.pos_in[lo:hi]
+                        else:
+                            pos = sh.pos_in
+                        sh.rng[lo:hi].copy_(self.h_rng[g_lo:g_hi], non_blocking=True)
+                        o = engine.optimize_on_device(
+                            sh.dtopo, pos, hi - lo, sh.rng[lo:hi], self.params, self.num_steps,
+                            self.precision, threads_per_chain=self.threads_per_chain, out=sh.out_slice(lo, hi),
+                        )
+                        self.h_pos_out[g_lo:g_hi].copy_(o.positions, non_blocking=True)
+                        self.h_f64[0, g_lo:g_hi].copy_(o.system_potential, non_blocking=True)
+                        self.h_f64[1, g_lo:g_hi].copy_(o.nonbonded_potential, non_blocking=True)
+                        self.h_f64[2, g_lo:g_hi].copy_(o.max_bond_distance, non_blocking=True)
+                        self.h_i32[0, g_lo:g_hi].copy_(o.n_accepted, non_blocking=True)
+                        self.h_i32[1, g_lo:g_hi].copy_(o.last_step_info, non_blocking=True)
+                        self.h_pairs[g_lo:g_hi].copy_(o.pair_evals, non_blocking=True)
+        for sh in self.shards:
+            for st in sh.streams:
+                st.synchronize()
+                torch.cuda.current_stream(sh.device).wait_stream(st)
+        return (self.h_pos_out.numel() * self.h_pos_out.element_size() + self.h_f64.numel() * 8
+                + self.h_i32.numel() * 4 + self.h_pairs.numel() * 8)
+
     def run(self, seeds: Sequence[int] | None = None, positions=None,
             rng_words: np.ndarray | None = None) -> BatchResult:
-        """Host buffers in, host buffers out: stage -> H2D -> kernel -> D2H."""
+        """Host buffers in, host buffers out: stage -> (H2D -> kernel -> D2H, pipelined by slice)."""
         start = time.perf_counter()
         h2d = self.stage_inputs(seeds, positions, rng_words)
-        self.upload()
-        self.launch()
-        d2h = self.download()
+        d2h = self._run_pipelined()
         return self.result(time.perf_counter() - start, h2d, d2h)

@@ -58,16 +58,20 @@ int mu_kind(double mu, int* mu_int) {
   return mch::MU_REAL;
 }
 
-int auto_threads(int n_atoms) {
+// Threads per chain when the caller does not say: small molecules share an SM between
+// several chains (<= 128 threads each); once one chain's shared memory takes more than half an
+// SM, that chain gets as many warps as the register file allows.
+int auto_threads(int n_atoms, int smem_bytes, int compute_dtype) {
   if (n_atoms <= 128) return 32;
   if (n_atoms <= 384) return 64;
-  if (n_atoms <= 3072) return 128;
-  return 256;
+  if (2 * smem_bytes <= kMaxSmem) return 128;
+  return compute_dtype == MCH_F64 ? 512 : 1024;
 }
 
-int check_threads(int requested, int n_atoms, int* out) {
-  int t = requested > 0 ? requested : auto_threads(n_atoms);
-  if (t % 32 != 0 || t < 32 || t > 256) return fail(MCH_ERR_INVALID, "threads must be a multiple of 32 in [32, 256], got %d", t);
+int check_threads(int requested, int fallback, int limit, int* out) {
+  int t = requested > 0 ? requested : fallback;
+  if (t % 32 != 0 || t < 32 || t > limit)
+    return fail(MCH_ERR_INVALID, "threads must be a multiple of 32 in [32, %d], got %d", limit, t);
   *out = t;
   return MCH_OK;
 }
@@ -174,11 +178,12 @@ int mch_optimize_batch(const mch_optimize_desc* d, void* stream) {
   if (!d->pos_in || !d->pos_out || !d->perm || !d->su_offsets || !d->bonds || !d->bond_su || !d->rng_state ||
       !d->system_potential || !d->nonbonded_potential || !d->max_bond_distance || !d->n_accepted || !d->last_step_info)
     return fail(MCH_ERR_INVALID, "mch_optimize_batch: null required pointer");
-  int threads;
-  int rc = check_threads(d->threads_per_chain, d->n_atoms, &threads);
-  if (rc != MCH_OK) return rc;
   const int smem = mch_optimize_smem_bytes(d->n_atoms, d->n_subunits, d->n_bonds, d->max_subunit_atoms, d->compute_dtype);
   if (smem < 0) return smem;
+  int threads;
+  int rc = check_threads(d->threads_per_chain, auto_threads(d->n_atoms, smem, d->compute_dtype),
+                         d->compute_dtype == MCH_F64 ? 512 : 1024, &threads);
+  if (rc != MCH_OK) return rc;
 
   mch::OptArgs a;
   a.pos_in = d->pos_in; a.pos_in_stride = d->pos_in_chain_stride; a.pos_out = d->pos_out;
@@ -238,7 +243,7 @@ int mch_collapse_batch(const mch_collapse_desc* d, void* stream) {
     return fail(MCH_ERR_INVALID, "mch_collapse_batch: trace buffers need trace_capacity > 0");
   if (d->n_atoms > (1 << 20) || d->n_subunits > (1 << 16)) return fail(MCH_ERR_TOO_LARGE, "molecule too large");
   int threads;
-  int rc = check_threads(d->threads_per_mol, d->n_atoms, &threads);
+  int rc = check_threads(d->threads_per_mol, d->n_atoms <= 128 ? 32 : (d->n_atoms <= 384 ? 64 : (d->n_atoms <= 3072 ? 128 : 256)), 256, &threads);
   if (rc != MCH_OK) return rc;
   const mch::ColLayout L = mch::col_layout(d->n_atoms, d->n_subunits, d->n_bonds, d->compute_dtype == MCH_F64 ? 8 : 4);
   if (L.total > kMaxSmem) return fail(MCH_ERR_TOO_LARGE, "molecule needs %d B of shared memory (limit %d)", L.total, kMaxSmem);

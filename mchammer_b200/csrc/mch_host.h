@@ -38,8 +38,8 @@ int launch_optimize_nt(int mk, const OptArgs& a, int threads, int smem, cudaStre
 
 template <typename T, typename Tio>
 int launch_optimize_io(int mk, const OptArgs& a, int threads, int smem, cudaStream_t s) {
-  return threads <= 128 ? launch_optimize_nt<T, Tio, 128>(mk, a, threads, smem, s)
-                        : launch_optimize_nt<T, Tio, 256>(mk, a, threads, smem, s);
+  return threads <= small_block<T>() ? launch_optimize_nt<T, Tio, small_block<T>()>(mk, a, threads, smem, s)
+                                     : launch_optimize_nt<T, Tio, large_block<T>()>(mk, a, threads, smem, s);
 }
 
 }  // namespace mch

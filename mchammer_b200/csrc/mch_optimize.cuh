@@ -126,13 +126,20 @@ constexpr int REGROUP_SMALL = 64;
 #define MCH_F32_THREADS_PER_SM 768  // 80 registers per thread, 6 chains (24 warps) per SM: measured best
 #endif
 
-// NTMAX: largest block this instantiation may be launched with.  fp32: 1024 / NTMAX blocks
-// per SM caps the kernel at 64 registers per thread, i.e. 32 resident warps per SM, so the
-// control section of one chain (a single warp, latency bound) is covered by the pair sweeps
-// of the other resident chains.  fp64 needs twice the registers for the same column tile
-// (128 per thread, 16 resident warps).
+// NTMAX: largest block this instantiation may be launched with.  Two instantiations per
+// compute type: a small-block one for chains that share an SM with others (fp32: 128
+// threads, MCH_F32_THREADS_PER_SM / 128 chains per SM -> 80 registers; fp64: 4 x 128, 128
+// registers) and a large-block one for molecules whose shared-memory footprint leaves room
+// for a single chain per SM (fp32: up to 1024 threads at 64 registers; fp64: up to 512 at
+// 128), so that one chain can still fill the SM's warp slots.
+template <typename T> constexpr int small_block() { return 128; }
+template <typename T> constexpr int large_block() { return sizeof(T) == 4 ? 1024 : 512; }
+template <typename T, int NTMAX> constexpr int min_blocks_per_sm() {
+  return NTMAX == small_block<T>() ? (sizeof(T) == 4 ? MCH_F32_THREADS_PER_SM : 512) / NTMAX : 1;
+}
+
 template <typename T, typename Tio, int MUK, int NTMAX>
-__global__ void __launch_bounds__(NTMAX, (sizeof(T) == 4 ? MCH_F32_THREADS_PER_SM : 512) / NTMAX)
+__global__ void __launch_bounds__(NTMAX, (min_blocks_per_sm<T, NTMAX>()))
 mch_optimize_kernel(const __grid_constant__ OptArgs a) {
   extern __shared__ __align__(32) unsigned char smem[];
   const int c = blockIdx.x;

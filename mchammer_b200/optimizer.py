@@ -231,6 +231,7 @@ class Optimizer:
         io_dtype=np.float64,
         per_chain_positions: bool = False,
         threads_per_chain: int = 0,
+        n_slices: int = 0,
     ) -> BatchPlan:
         """Lower the topology once and allocate pinned/device buffers for ``n_chains`` chains.
 
@@ -246,7 +247,7 @@ class Optimizer:
             devices = [self._torch_device().index]
         return BatchPlan(
             topo, mol.get_position_matrix(), self._params(), self._num_steps, self._precision,
-            n_chains, list(devices), io_dtype, per_chain_positions, threads_per_chain,
+            n_chains, list(devices), io_dtype, per_chain_positions, threads_per_chain, n_slices,
         )
 
     def get_results_batch(
