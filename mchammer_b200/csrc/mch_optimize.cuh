@@ -90,7 +90,8 @@ MCH_HD OptLayout opt_layout(int N, int S, int B, int max_su, int tsize) {
   L.x = o; o += np * tsize;
   L.y = o; o += np * tsize;
   L.z = o; o += np * tsize;
-  L.colsum = o; L.colsum_stride = np * (tsize < 4 ? 4 : tsize); o += 2 * L.colsum_stride;  // double buffered
+  L.colsum = o; L.colsum_stride = np * (tsize < 4 ? 4 : tsize);
+  o += (MCH_DEFER ? 2 : 1) * L.colsum_stride;  // double buffered when control work is deferred
   o = align_up(o, 32);
   L.rows = o; o += (max_su + 4) * 4 * tsize;  // + far-away padding row + prefetch overrun
   o = align_up(o, 16);
@@ -375,7 +376,7 @@ mch_optimize_kernel(const __grid_constant__ OptArgs a) {
     const int n = fill_rows(ms, tvx, tvy, tvz);                    // :248-252  (pos - vector)
     if (lane == 0) {
       ctl->nrows = n; ctl->c0 = 0; ctl->g0 = suoff[ms]; ctl->g1 = suoff[ms + 1]; ctl->c1 = N; ctl->ms = ms;
-      ctl->buf = buf;
+      ctl->buf = kDefer ? buf : 0;
     }
   };
   // exp(x) > r for x <= 0, r in [0, 1): decided by a fast fp32 exponential whenever it is
@@ -527,7 +528,7 @@ mch_optimize_kernel(const __grid_constant__ OptArgs a) {
       }
       __syncwarp();
       info = kb | ((ok ? 1 : 0) << 16) | (kind << 17) | (ms << 18);
-      d_accepted = ok; d_ms = ms; d_buf = step & 1; d_step = step;
+      d_accepted = ok; d_ms = ms; d_buf = kDefer ? (step & 1) : 0; d_step = step;
       if (!kDefer) {
         if (ok) { regroup(colsum + d_buf * colsum_stride, ms, 0); refresh_erow(); }
         d_accepted = false;

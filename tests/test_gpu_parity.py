@@ -296,6 +296,66 @@ def test_fp32_expanded_form_energy_accuracy():
         assert np.isclose(ref64.nonbonded_potential[0], want_unb, rtol=1e-12, atol=0)
 
 
+@pytest.mark.parametrize("case", ["benzene_mu2p5", "benzene_mu6"])
+def test_fp32_mode_other_exponents(case):
+    # fp32 pair terms for real mu (exp2/log2) and integer mu != 3 (square-and-multiply)
+    g = load_golden(case)
+    opt = golden_optimizer(g, precision="fp32")
+    _, result = opt.get_trajectory(golden_molecule(g), golden_bonds(g), golden_subunits(g))
+    props = [p for _, p in result.get_steps_properties()]
+    passed = np.array([-1 if p["passed"] is None else int(p["passed"]) for p in props])
+    same = passed == g["passed"]
+    prefix = len(same) if same.all() else int(np.argmin(same))
+    assert prefix >= 20
+    u = np.array([p["system_potential"] for p in props])[:prefix]
+    assert rel_close(u, g["system_potential"][:prefix], RTOL32)
+
+
+def test_batch_io_float32_and_two_shards_on_one_device():
+    mol, long_bonds, subunits = synthetic.cube_cage(atoms_per_subunit=10, seed=4, spread=6.0)
+    seeds = list(range(40, 47))
+    opt = mch.Optimizer(step_size=0.25, target_bond_length=1.2, num_steps=50)
+    whole = opt.get_results_batch(mol, long_bonds, subunits, seeds=seeds)
+    # the same chains split over two shards (both on device 0): identical results, host gather
+    split = opt.get_results_batch(mol, long_bonds, subunits, seeds=seeds, devices=[0, 0])
+    assert np.array_equal(split.positions, whole.positions)
+    assert np.array_equal(split.system_potential, whole.system_potential)
+    assert np.array_equal(split.n_accepted, whole.n_accepted)
+    # float32 I/O with fp64 compute: inputs/outputs rounded to fp32, arithmetic unchanged
+    f32 = opt.get_results_batch(mol, long_bonds, subunits, seeds=seeds, io_dtype=np.float32)
+    assert f32.positions.dtype == np.float32
+    start32 = mol.get_position_matrix().astype(np.float32).astype(np.float64)
+    p = orc.OptimizerParams(step_size=0.25, target_bond_length=1.2, num_steps=50)
+    want = orc.optimizer_run(start32, long_bonds, subunits, p, np.random.default_rng(seeds[0]))
+    assert rel_close(f32.system_potential[0], want.system_potential[-1], RTOL64)
+    assert np.allclose(f32.positions[0], want.final_positions, rtol=0, atol=2e-6)
+    # a prepared plan can be re-run; slices of the pipelined run do not change results
+    plan = opt.prepare_batch(mol, long_bonds, subunits, len(seeds), n_slices=3)
+    again = plan.run(seeds=seeds).copy()
+    assert np.array_equal(again.positions, whole.positions)
+
+
+def test_single_subunit_and_intra_subunit_bond():
+    # every atom in one subunit: no cross pairs; moves translate the whole molecule rigidly,
+    # so the potential never changes -- the chain must still follow the reference exactly
+    rng = np.random.default_rng(12)
+    pos = rng.normal(scale=2.5, size=(9, 3))
+    mol = mch.Molecule(atoms=[mch.Atom(i, "C") for i in range(9)], bonds=[], position_matrix=pos)
+    subunits = {0: list(range(9))}
+    long_bonds = ((0, 5), (3, 8))
+    opt = mch.Optimizer(step_size=0.2, target_bond_length=1.5, num_steps=30, random_seed=77)
+    out_mol, last = opt.get_result(mol, long_bonds, subunits)
+    p = orc.OptimizerParams(step_size=0.2, target_bond_length=1.5, num_steps=30)
+    want = orc.optimizer_run(pos, long_bonds, subunits, p, np.random.default_rng(77))
+    assert bool(last.passed) == bool(want.passed[-1])
+    assert rel_close(last.system_potential, want.system_potential[-1], RTOL64)
+    assert np.allclose(out_mol.get_position_matrix(), want.final_positions, rtol=RTOL64, atol=1e-9)
+    with pytest.raises(ValueError):
+        opt.get_result(mol, (), subunits)  # nothing to optimise (the reference's choice([]) raises too)
+    with pytest.raises(StopIteration):
+        opt.get_result(mol, long_bonds, {0: [0, 1, 2, 3, 4]})  # bond end in no subunit
+
+
 # ------------------------------------------------------------------------- properties at BASELINE size
 @pytest.mark.parametrize("precision,rtol,atol", [("fp64", 1e-9, 1e-9), ("fp32", 1e-4, 2e-4)])
 def test_full_size_cage_properties(precision, rtol, atol):
