@@ -58,14 +58,15 @@ int mu_kind(double mu, int* mu_int) {
   return mch::MU_REAL;
 }
 
-// Threads per chain when the caller does not say: small molecules share an SM between
-// several chains (<= 128 threads each); once one chain's shared memory takes more than half an
-// SM, that chain gets as many warps as the register file allows.
+// Threads per chain when the caller does not say.  Measured on B200:
+// chains that share an SM run best with few warps each -- every warp of a chain but one
+// idles while the chain's control section runs, and with one or two warps per chain that
+// loss (almost) disappears while 8-10 resident chains still keep the pipes busy.  A chain
+// whose shared memory takes more than half an SM is alone there and gets 16 warps.
 int auto_threads(int n_atoms, int smem_bytes, int compute_dtype) {
   if (n_atoms <= 128) return 32;
-  if (n_atoms <= 384) return 64;
-  if (2 * smem_bytes <= kMaxSmem) return 128;
-  return compute_dtype == MCH_F64 ? 512 : 1024;
+  if (2 * smem_bytes <= kMaxSmem) return compute_dtype == MCH_F64 ? 128 : 64;
+  return 512;
 }
 
 int check_threads(int requested, int fallback, int limit, int* out) {

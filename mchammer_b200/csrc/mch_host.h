@@ -38,6 +38,8 @@ int launch_optimize_nt(int mk, const OptArgs& a, int threads, int smem, cudaStre
 
 template <typename T, typename Tio>
 int launch_optimize_io(int mk, const OptArgs& a, int threads, int smem, cudaStream_t s) {
+  if (sizeof(T) == 4 && threads <= 32) return launch_optimize_nt<T, Tio, 32>(mk, a, threads, smem, s);
+  if (sizeof(T) == 4 && threads <= 64) return launch_optimize_nt<T, Tio, 64>(mk, a, threads, smem, s);
   return threads <= small_block<T>() ? launch_optimize_nt<T, Tio, small_block<T>()>(mk, a, threads, smem, s)
                                      : launch_optimize_nt<T, Tio, large_block<T>()>(mk, a, threads, smem, s);
 }

@@ -136,7 +136,9 @@ constexpr int REGROUP_SMALL = 64;
 template <typename T> constexpr int small_block() { return 128; }
 template <typename T> constexpr int large_block() { return sizeof(T) == 4 ? 1024 : 512; }
 template <typename T, int NTMAX> constexpr int min_blocks_per_sm() {
-  return NTMAX == small_block<T>() ? (sizeof(T) == 4 ? MCH_F32_THREADS_PER_SM : 512) / NTMAX : 1;
+  return NTMAX == 32 ? 10  // one-warp chains
+         : NTMAX == 64 ? 8   // two-warp chains: shared memory allows 8 per SM, so 128 registers each
+         : NTMAX == small_block<T>() ? (sizeof(T) == 4 ? MCH_F32_THREADS_PER_SM : 512) / NTMAX : 1;
 }
 
 template <typename T, typename Tio, int MUK, int NTMAX>
