@@ -13,14 +13,14 @@ int launch_optimize_f32(bool io_f64, int mk, const OptArgs& a, int threads, int 
 // ---------------------------------------------------------------------------------------
 template <int NTMAX>
 __global__ void __launch_bounds__(NTMAX, 1024 / NTMAX)
-probe_sweep_kernel(int iters, int with_barrier, int nrows_real, int ncols, float* sink) {
+probe_sweep_kernel(int iters, int with_barrier, int nrows_real, int ncols, float* sink, int store) {
   extern __shared__ __align__(32) unsigned char smem[];
   const int N = 1000;
   float* X = reinterpret_cast<float*>(smem);
   float* Y = X + 1008;
   float* Z = Y + 1008;
-  float* colsum = Z + 1008;
-  Row4<float>* Q = reinterpret_cast<Row4<float>*>(colsum + 2016);
+  float* colsum = Z + 1008;  // only present when store != 0
+  Row4<float>* Q = reinterpret_cast<Row4<float>*>(colsum + (store ? 2016 : 0));
   for (int n = threadIdx.x; n < N; n += blockDim.x) {
     X[n] = 0.013f * n + 0.5f * blockIdx.x; Y[n] = 7.0f - 0.009f * n; Z[n] = 0.003f * n * (n & 7);
   }
@@ -36,20 +36,23 @@ probe_sweep_kernel(int iters, int with_barrier, int nrows_real, int ncols, float
   double total = 0.0;
   for (int it = 0; it < iters; ++it) {
     Cols cols{0, 0, 50, 50 + ncols};
-    total += pair_sweep<float, MU_3, false, true, kXF>(Q, np, X, Y, Z, colsum + (it & 1) * 1008, cols, term, ctr);
+    if (store) total += pair_sweep<float, MU_3, false, true, kXF>(Q, np, X, Y, Z, colsum + (it & 1) * 1008, cols, term, ctr);
+    else total += pair_sweep<float, MU_3, false, false, kXF>(Q, np, X, Y, Z, (float*)nullptr, cols, term, ctr);
     if (with_barrier) __syncthreads();
   }
   if (total == -1.2345) *sink = (float)total;
 }
 
 int launch_probe_sweep(int blocks, int threads, int iters, int with_barrier, int nrows, int ncols, float* sink, cudaStream_t s) {
-  const int smem = (1008 * 3 + 2016) * 4 + 64 * 16 + 256;
+  const int store = with_barrier < 2 ? 1 : 0;  // with_barrier 2/3 = 0/1 without the column-sum stores
+  with_barrier &= 1;
+  const int smem = (1008 * 3 + (store ? 2016 : 0)) * 4 + 64 * 16 + 256;
   if (threads <= 128) {
     cudaFuncSetAttribute(probe_sweep_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    probe_sweep_kernel<128><<<blocks, threads, smem, s>>>(iters, with_barrier, nrows, ncols, sink);
+    probe_sweep_kernel<128><<<blocks, threads, smem, s>>>(iters, with_barrier, nrows, ncols, sink, store);
   } else {
     cudaFuncSetAttribute(probe_sweep_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    probe_sweep_kernel<256><<<blocks, threads, smem, s>>>(iters, with_barrier, nrows, ncols, sink);
+    probe_sweep_kernel<256><<<blocks, threads, smem, s>>>(iters, with_barrier, nrows, ncols, sink, store);
   }
   return cudaGetLastError() == cudaSuccess ? 0 : -3;
 }
