@@ -38,7 +38,7 @@ struct ColArgs {
   int trace_cap;
 };
 
-struct ColLayout { int x, y, z, suof, suoff, nheavy, bslot, csum, vec, wsum, flag, total; };
+struct ColLayout { int x, y, z, suof, suoff, nheavy, bslot, csum, vec, wsum, total; };
 
 MCH_HD ColLayout col_layout(int N, int S, int B, int tsize) {
   ColLayout L;
@@ -55,7 +55,6 @@ MCH_HD ColLayout col_layout(int N, int S, int B, int tsize) {
   L.csum = o; o += S * 3 * 8;
   L.vec = o; o += S * 3 * 8;
   L.wsum = o; o += 3 * 32 * 8;
-  L.flag = o; o += 64;
   L.total = align_up(o, 16);
   return L;
 }
@@ -81,7 +80,6 @@ mch_collapse_kernel(const __grid_constant__ ColArgs a) {
   double* csum = reinterpret_cast<double*>(smem + L.csum);
   double* vec = reinterpret_cast<double*>(smem + L.vec);
   double* wsum = reinterpret_cast<double*>(smem + L.wsum);
-  double* flag = reinterpret_cast<double*>(smem + L.flag);  // [0] min distance, [1] scratch
 
   // ------------------------------------------------------------ prologue
   for (int n = tid; n < N; n += nt) suof[a.perm[n]] = n;  // inverse permutation, temporarily

@@ -18,15 +18,21 @@
 //           the optional trace/trajectory records.
 //
 // Algorithm per step (exact reference order of random draws)
-//   control warp : draws -> translation vector -> Q = P[ms] - tv -> bond energies of the
-//                  trial geometry
-//   all warps    : sum_{i in ms, j not in ms} r_ij^-mu   (pair_sweep; n_ms x (N - n_ms))
-//   control warp : dU_nb = eps sigma^mu * sum - sum_t E[ms][t];  Metropolis test;
-//                  accept -> P[ms] = Q, refresh row/column ms of E from the per-column
-//                  sums;  reject -> P untouched (fp32) or the reference's inexact undo
-//                  (p - v) + v (fp64 parity mode, optimizer.py:269-277).
+//   control warp : draws -> translation vector -> encoded rows Q of P[ms] - tv    [barrier A]
+//   all warps    : sum_{i in ms, j not in ms} r_ij^-mu  (pair_sweep: n_ms x (N - n_ms) terms;
+//                  per-column sums to shared memory, per-warp totals)             [barrier B]
+//   control warp : dU_nb = eps sigma^mu * total - sum_t E[ms][t];  Metropolis test;
+//                  accept -> P[ms] -= tv;  reject -> P untouched (fp32) or the reference's
+//                  inexact undo (p - v) + v (fp64 parity mode, optimizer.py:269-277);
+//                  then the next proposal.
+//   The half of the control work that the next sweep does not depend on -- rebuilding
+//   row/column ms of E from the column sums after an accept, the bond energy of the trial
+//   geometry, trace records -- is DEFERRED: warp 0 runs it after barrier A, under the other
+//   warps' sweep, reading the previous sweep's column sums from the other of two buffers.
 //   Intra-subunit pairs are constant under rigid moves; they are evaluated once at step 0
 //   and carried in U_nb (the reference re-sums them every step, optimizer.py:114-120).
+//   The control warp's registers (RNG state, potentials, move) are parked in shared memory
+//   while it sweeps, so nothing is spilled around the sweep-tile calls.
 #pragma once
 
 #include "mch_device.cuh"
@@ -109,7 +115,6 @@ MCH_HD OptLayout opt_layout(int N, int S, int B, int max_su, int tsize) {
   return L;
 }
 
-
 #ifdef __CUDACC__
 
 template <typename Tio> MCH_D double load_io(const void* base, long long idx) {
@@ -124,15 +129,16 @@ template <typename Tio> MCH_D void store_io(void* base, long long idx, double v)
 constexpr int REGROUP_SMALL = 64;
 
 #ifndef MCH_F32_THREADS_PER_SM
-#define MCH_F32_THREADS_PER_SM 768  // 80 registers per thread, 6 chains (24 warps) per SM: measured best
+#define MCH_F32_THREADS_PER_SM 768  // 128-thread fp32 blocks: 80 registers per thread, 6 chains per SM
 #endif
 
-// NTMAX: largest block this instantiation may be launched with.  Two instantiations per
-// compute type: a small-block one for chains that share an SM with others (fp32: 128
-// threads, MCH_F32_THREADS_PER_SM / 128 chains per SM -> 80 registers; fp64: 4 x 128, 128
-// registers) and a large-block one for molecules whose shared-memory footprint leaves room
-// for a single chain per SM (fp32: up to 1024 threads at 64 registers; fp64: up to 512 at
-// 128), so that one chain can still fill the SM's warp slots.
+// NTMAX: largest block an instantiation may be launched with; together with the minimum
+// number of resident blocks it fixes the register budget.  Chains that share an SM:
+//   32 threads (10 chains/SM), 64 threads (8 chains/SM, 128 registers -- the S1 default),
+//   128 threads (fp32: MCH_F32_THREADS_PER_SM / 128 = 6 chains, 80 registers; fp64: 4 chains,
+//   128 registers).  A molecule whose shared memory leaves room for one chain per SM uses the
+//   large-block instantiation (fp32: up to 1024 threads at 64 registers; fp64: up to 512 at 128)
+//   so that the single chain can still fill the SM's warp slots.
 template <typename T> constexpr int small_block() { return 128; }
 template <typename T> constexpr int large_block() { return sizeof(T) == 4 ? 1024 : 512; }
 template <typename T, int NTMAX> constexpr int min_blocks_per_sm() {
