@@ -61,12 +61,13 @@ int mu_kind(double mu, int* mu_int) {
 // Threads per chain when the caller does not say.  Measured on B200:
 // chains that share an SM run best with few warps each -- every warp of a chain but one
 // idles while the chain's control section runs, and with one or two warps per chain that
-// loss (almost) disappears while 8-10 resident chains still keep the pipes busy.  A chain
-// whose shared memory takes more than half an SM is alone there and gets 16 warps.
+// loss (almost) disappears while 8-10 resident chains still keep the pipes busy.  Large
+// molecules (one or two chains per SM) get 16 / 8 warps per chain instead.
 int auto_threads(int n_atoms, int smem_bytes, int compute_dtype) {
   if (n_atoms <= 128) return 32;
-  if (2 * smem_bytes <= kMaxSmem) return compute_dtype == MCH_F64 ? 128 : 64;
-  return 512;
+  const int chains_per_sm = kMaxSmem / smem_bytes;
+  if (chains_per_sm >= 3) return compute_dtype == MCH_F64 ? 128 : 64;
+  return chains_per_sm == 2 ? 256 : 512;
 }
 
 int check_threads(int requested, int fallback, int limit, int* out) {
@@ -158,14 +159,32 @@ extern "C" {
 const char* mch_last_error(void) { return g_error; }
 int mch_version(void) { return 100; }
 
+namespace {
+// Shared memory of one chain and whether the control work is deferred (second column-sum
+// buffer).  Deferral hides the chain's serial control section, which matters for small and
+// medium molecules; for a large molecule (fewer than three chains per SM) the control section
+// is negligible next to the sweep, and the buffer is dropped when it would cost a resident
+// chain (the 5004-atom cage: 115 KB with it -> one chain per SM, 95 KB without -> two) or
+// would not fit at all.
+int plan_chain_smem(int n_atoms, int n_subunits, int n_bonds, int max_su, int compute_dtype, int* defer) {
+  const int tsize = compute_dtype == MCH_F64 ? 8 : 4;
+  const int with = mch::opt_layout(n_atoms, n_subunits, n_bonds, max_su, tsize, 1).total;
+  const int without = mch::opt_layout(n_atoms, n_subunits, n_bonds, max_su, tsize, 0).total;
+  const bool keep = with <= kMaxSmem && (kMaxSmem / with >= 3 || kMaxSmem / with == kMaxSmem / without);
+  *defer = keep ? 1 : 0;
+  return keep ? with : without;
+}
+}  // namespace
+
 int mch_optimize_smem_bytes(int n_atoms, int n_subunits, int n_bonds, int max_subunit_atoms, int compute_dtype) {
   if (n_atoms <= 0 || n_subunits <= 0 || n_bonds < 0 || max_subunit_atoms <= 0 || !dtype_ok(compute_dtype))
     return fail(MCH_ERR_INVALID, "mch_optimize_smem_bytes: bad sizes");
   const long long est = 4LL * n_atoms * 8 + 8LL * n_subunits * n_subunits;
   if (est > (1LL << 30)) return fail(MCH_ERR_TOO_LARGE, "molecule too large");
-  const mch::OptLayout L = mch::opt_layout(n_atoms, n_subunits, n_bonds, max_subunit_atoms, compute_dtype == MCH_F64 ? 8 : 4);
-  if (L.total > kMaxSmem) return fail(MCH_ERR_TOO_LARGE, "chain needs %d B of shared memory (limit %d)", L.total, kMaxSmem);
-  return L.total;
+  int defer;
+  const int total = plan_chain_smem(n_atoms, n_subunits, n_bonds, max_subunit_atoms, compute_dtype, &defer);
+  if (total > kMaxSmem) return fail(MCH_ERR_TOO_LARGE, "chain needs %d B of shared memory (limit %d)", total, kMaxSmem);
+  return total;
 }
 
 int mch_optimize_batch(const mch_optimize_desc* d, void* stream) {
@@ -199,6 +218,7 @@ int mch_optimize_batch(const mch_optimize_desc* d, void* stream) {
   a.trace_f = d->trace_potentials; a.trace_i = d->trace_info; a.traj = d->trajectory;
   a.pairs = reinterpret_cast<unsigned long long*>(d->pair_evals);
   a.inexact_undo = d->inexact_undo;
+  (void)plan_chain_smem(d->n_atoms, d->n_subunits, d->n_bonds, d->max_subunit_atoms, d->compute_dtype, &a.defer);
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
   const bool io_f64 = d->io_dtype == MCH_F64;
   return d->compute_dtype == MCH_F64 ? mch::launch_optimize_f64(io_f64, mk, a, threads, smem, s)

@@ -63,6 +63,7 @@ struct OptArgs {
   void* traj;                // [C][num_steps][N][3] io dtype or null
   unsigned long long* pairs; // [C] or null: pair terms evaluated
   int inexact_undo;          // 1: reproduce (p - v) + v on reject (fp64 parity)
+  int defer;                 // 1: deferred control work + second column-sum buffer (see header)
 };
 
 struct Ctl {
@@ -89,7 +90,7 @@ struct OptLayout {
 
 MCH_HD int align_up(int v, int a) { return (v + a - 1) / a * a; }
 
-MCH_HD OptLayout opt_layout(int N, int S, int B, int max_su, int tsize) {
+MCH_HD OptLayout opt_layout(int N, int S, int B, int max_su, int tsize, int defer) {
   OptLayout L;
   const int np = align_up(N, 8);
   int o = 0;
@@ -97,7 +98,7 @@ MCH_HD OptLayout opt_layout(int N, int S, int B, int max_su, int tsize) {
   L.y = o; o += np * tsize;
   L.z = o; o += np * tsize;
   L.colsum = o; L.colsum_stride = np * (tsize < 4 ? 4 : tsize);
-  o += (MCH_DEFER ? 2 : 1) * L.colsum_stride;  // double buffered when control work is deferred
+  o += (defer ? 2 : 1) * L.colsum_stride;  // double buffered when control work is deferred
   o = align_up(o, 32);
   L.rows = o; o += (max_su + 4) * 4 * tsize;  // + far-away padding row + prefetch overrun
   o = align_up(o, 16);
@@ -156,7 +157,7 @@ mch_optimize_kernel(const __grid_constant__ OptArgs a) {
   const int nt = blockDim.x, nwarps = nt >> 5;
   const int N = a.N, S = a.S, B = a.B;
 
-  const OptLayout L = opt_layout(N, S, B, a.max_su, (int)sizeof(T));
+  const OptLayout L = opt_layout(N, S, B, a.max_su, (int)sizeof(T), a.defer);
   T* X = reinterpret_cast<T*>(smem + L.x);
   T* Y = reinterpret_cast<T*>(smem + L.y);
   T* Z = reinterpret_cast<T*>(smem + L.z);
@@ -223,7 +224,7 @@ mch_optimize_kernel(const __grid_constant__ OptArgs a) {
   // (uniform across the 32 lanes of warp 0; other warps never read it)
   constexpr bool kFast = sizeof(T) == 4;  // fp32 mode: cheaper centroid bookkeeping
   constexpr bool kXF = kFast && (MCH_XF != 0);  // expanded-form squared distances (mch_device.cuh)
-  constexpr bool kDefer = (MCH_DEFER != 0);
+  const bool kDefer = a.defer != 0;  // host policy: off when the second buffer would cost a resident chain
   Pcg64 rng;  // loaded after step 0 (nothing of the control state is live across the step-0 sweeps)
   rng.hi = rng.lo = rng.inc_hi = rng.inc_lo = 0ULL; rng.has32 = rng.half = 0u;
   double U = 0.0, Unb = 0.0, Ub_trial = 0.0;
