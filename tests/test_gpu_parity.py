@@ -356,6 +356,42 @@ def test_single_subunit_and_intra_subunit_bond():
         opt.get_result(mol, long_bonds, {0: [0, 1, 2, 3, 4]})  # bond end in no subunit
 
 
+def test_large_cage_against_oracle_both_precisions():
+    # BASELINE config 5 geometry (5004 atoms, 36 subunits incl. 12 one-atom nodes): the fp64
+    # chain fills an SM alone; the fp32 chain runs without the deferred-control buffer so that
+    # two fit (csrc/mch_api.cu plan_chain_smem).  Few steps: the oracle needs ~0.25 s per step.
+    mol, long_bonds, subunits = synthetic.cuboctahedron_cage()
+    steps = 9
+    p = orc.OptimizerParams(step_size=0.25, target_bond_length=1.2, num_steps=steps)
+    want = orc.optimizer_run(mol.get_position_matrix(), long_bonds, subunits, p, np.random.default_rng(21))
+    exact = mch.Optimizer(0.25, 1.2, steps, precision="fp64").get_results_batch(mol, long_bonds, subunits, seeds=[21, 22])
+    assert int(exact.n_accepted[0]) == int((want.passed == 1).sum())
+    assert rel_close(exact.system_potential[0], want.system_potential[-1], RTOL64)
+    assert np.allclose(exact.positions[0], want.final_positions, rtol=RTOL64, atol=1e-9)
+    fast = mch.Optimizer(0.25, 1.2, steps, precision="fp32").get_results_batch(mol, long_bonds, subunits, seeds=[21, 22])
+    assert int(fast.n_accepted[0]) == int((want.passed == 1).sum())
+    assert rel_close(fast.system_potential[0], want.system_potential[-1], RTOL32)
+    assert np.allclose(fast.positions[0], want.final_positions, rtol=0, atol=1e-3)
+
+
+@pytest.mark.parametrize("precision", ["fp64", "fp32"])
+def test_threads_per_chain_does_not_change_the_chain(precision):
+    # block size only changes how the pair sum is partitioned (rounding at the 1e-16 / 1e-7 level)
+    mol, long_bonds, subunits = synthetic.cube_cage(atoms_per_subunit=24, seed=6, spread=8.0)
+    opt = mch.Optimizer(0.25, 1.2, 60, precision=precision)
+    seeds = [3, 4, 5]
+    base = opt.get_results_batch(mol, long_bonds, subunits, seeds=seeds, threads_per_chain=32)
+    limit = 512 if precision == "fp64" else 1024
+    for threads in (64, 96, 128, 256, limit):
+        got = opt.get_results_batch(mol, long_bonds, subunits, seeds=seeds, threads_per_chain=threads)
+        assert np.array_equal(got.n_accepted, base.n_accepted), threads
+        assert rel_close(got.system_potential, base.system_potential, 1e-12 if precision == "fp64" else 1e-5)
+    with pytest.raises(mch.native.NativeLibraryError):
+        opt.get_results_batch(mol, long_bonds, subunits, seeds=seeds, threads_per_chain=limit + 32)
+    with pytest.raises(mch.native.NativeLibraryError):
+        opt.get_results_batch(mol, long_bonds, subunits, seeds=seeds, threads_per_chain=48)
+
+
 # ------------------------------------------------------------------------- properties at BASELINE size
 @pytest.mark.parametrize("precision,rtol,atol", [("fp64", 1e-9, 1e-9), ("fp32", 1e-4, 2e-4)])
 def test_full_size_cage_properties(precision, rtol, atol):
