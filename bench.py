@@ -261,7 +261,7 @@ def probe_pipe_peak(torch, dtype_code: int, device) -> float:
         e1.record()
         e1.synchronize()
         ms = e0.elapsed_time(e1)
-        per_op = 1.0 if dtype_code == 2 else 2.0
+        per_op = {2: 1.0, 3: 4.0}.get(dtype_code, 2.0)  # MUFU: results; FFMA2: 2 lanes x 2 flops
         best = max(best, per_op * 8.0 * iters * blocks * threads / (ms * 1e-3) / 1e12)
     return best
 
@@ -358,6 +358,8 @@ def cuda_arm(args):
         peaks, peaks_src = measured_peaks()
         dtype_code = native.MCH_F32 if args.precision == "fp32" else native.MCH_F64
         pipe_peak = probe_pipe_peak(torch, dtype_code, device)
+        if args.precision == "fp32":  # the packed FFMA2 stream is the faster of the two fp32 probes
+            pipe_peak = max(pipe_peak, probe_pipe_peak(torch, 3, device))
         mufu_peak = probe_pipe_peak(torch, 2, device) if args.precision == "fp32" else None
         launch_s = dev_seconds / args.steps
         achieved_tflops = FLOPS_PER_PAIR * pairs_per_launch / launch_s / 1e12
@@ -385,9 +387,11 @@ def cuda_arm(args):
                 "traffic": profiled_traffic(args.precision) if args.workload == "cube1000" and chains == 4096 else None,
                 "kernel": "mch_optimize_kernel",
                 "note": f"achieved = {FLOPS_PER_PAIR:.0f} flops/pair x {pairs_per_launch} pairs per launch / "
-                        "CUDA-event launch time; peak = dependent-FMA probe (mch_probe_fma) measured in this run; "
-                        "the kernel is bound by the CUDA-core FP pipe, not by HBM or tensor cores (SURVEY.md 8-d)",
+                        "CUDA-event launch time; peak = best dependent-FMA probe (mch_probe_fma: FFMA and packed "
+                        "FFMA2 streams) measured in this run; the kernel is bound by the CUDA-core pipes (FP32/FP64 "
+                        "FMA and, in fp32 mode, one MUFU.RSQ per pair), not by HBM or tensor cores (SURVEY.md 8-d)",
                 "mufu_rsqrt_per_s_peak": mufu_peak * 1e12 if mufu_peak else None,
+                "mufu_frac": pairs_per_launch / launch_s / (mufu_peak * 1e12) if mufu_peak else None,
                 "hbm": {"achieved_gbs": io_bytes / launch_s / 1e9, "peak_gbs": peaks.get("hbm_gbs"),
                         "peak_source": peaks_src},
             },

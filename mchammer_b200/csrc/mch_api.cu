@@ -31,6 +31,10 @@ int fail(int code, const char* fmt, ...) {
 namespace {
 using mch::fail;
 using mch::launch;
+using mch::f32x2;
+using mch::pack2;
+using mch::unpack2;
+using mch::fma2;
 
 constexpr int kMaxSmem = 227 * 1024;
 
@@ -67,7 +71,8 @@ int auto_threads(int n_atoms, int smem_bytes, int compute_dtype) {
   if (n_atoms <= 128) return 32;
   const int chains_per_sm = kMaxSmem / smem_bytes;
   if (chains_per_sm >= 3) return compute_dtype == MCH_F64 ? 128 : 64;
-  return chains_per_sm == 2 ? 256 : 512;
+  // two chains per SM: fill the register file (fp32: 2 x 512 x 64, fp64: 2 x 256 x 128)
+  return chains_per_sm == 2 && compute_dtype == MCH_F64 ? 256 : 512;
 }
 
 int check_threads(int requested, int fallback, int limit, int* out) {
@@ -111,6 +116,42 @@ __global__ void probe_rsqrt_kernel(int iters, float* sink) {
     a4 = rsqrtf(a4); a5 = rsqrtf(a5); a6 = rsqrtf(a6); a7 = rsqrtf(a7);
   }
   const float r = ((a0 + a1) + (a2 + a3)) + ((a4 + a5) + (a6 + a7));
+  if (r == -12345.678f) *sink = r;
+}
+
+// Issue-mix probes (profiles/probe_mix.py): 8 independent instructions per iteration.
+//   MODE 3: 8 FFMA2        MODE 4: 6 FFMA2 + 2 MUFU.RSQ
+//   MODE 5: 6 FFMA + 2 MUFU.RSQ     MODE 6: 12 FFMA + 2 MUFU.RSQ (the scalar work of mode 4)
+template <int MODE>
+__global__ void probe_mix_kernel(int iters, float* sink) {
+  const float t = 1e-3f * threadIdx.x;
+  f32x2 p[6];
+  float f[12], r0 = 1.5f + t, r1 = 2.5f + t;
+  const f32x2 m2 = pack2(0.999f, 0.998f), c2 = pack2(1e-3f, 2e-3f);
+#pragma unroll
+  for (int k = 0; k < 6; ++k) p[k] = pack2(t + k, t - k);
+#pragma unroll
+  for (int k = 0; k < 12; ++k) f[k] = t + 0.5f * k;
+  f32x2 q0 = pack2(t, 1.f), q1 = pack2(t, 2.f);
+  for (int i = 0; i < iters; ++i) {
+    if (MODE == 3 || MODE == 4) {
+#pragma unroll
+      for (int k = 0; k < 6; ++k) p[k] = fma2(p[k], m2, c2);
+    }
+    if (MODE == 3) { q0 = fma2(q0, m2, c2); q1 = fma2(q1, m2, c2); }
+    if (MODE == 5 || MODE == 6) {
+#pragma unroll
+      for (int k = 0; k < (MODE == 5 ? 6 : 12); ++k) f[k] = fmaf(f[k], 0.999f, 1e-3f);
+    }
+    if (MODE != 3) { r0 = rsqrtf(r0); r1 = rsqrtf(r1); }
+  }
+  float lo, hi, r = r0 + r1;
+#pragma unroll
+  for (int k = 0; k < 6; ++k) { unpack2(p[k], lo, hi); r += lo + hi; }
+  unpack2(q0, lo, hi); r += lo + hi;
+  unpack2(q1, lo, hi); r += lo + hi;
+#pragma unroll
+  for (int k = 0; k < 12; ++k) r += f[k];
   if (r == -12345.678f) *sink = r;
 }
 
@@ -330,7 +371,11 @@ int mch_probe_fma(int dtype, int blocks, int threads, int iters, float* sink, vo
   if (dtype == MCH_F64) probe_fma_kernel<double><<<blocks, threads, 0, s>>>(iters, sink);
   else if (dtype == MCH_F32) probe_fma_kernel<float><<<blocks, threads, 0, s>>>(iters, sink);
   else if (dtype == 2) probe_rsqrt_kernel<<<blocks, threads, 0, s>>>(iters, sink);
-  else return fail(MCH_ERR_INVALID, "mch_probe_fma: dtype must be 0 (f64 fma), 1 (f32 fma) or 2 (f32 rsqrt)");
+  else if (dtype == 3) probe_mix_kernel<3><<<blocks, threads, 0, s>>>(iters, sink);
+  else if (dtype == 4) probe_mix_kernel<4><<<blocks, threads, 0, s>>>(iters, sink);
+  else if (dtype == 5) probe_mix_kernel<5><<<blocks, threads, 0, s>>>(iters, sink);
+  else if (dtype == 6) probe_mix_kernel<6><<<blocks, threads, 0, s>>>(iters, sink);
+  else return fail(MCH_ERR_INVALID, "mch_probe_fma: dtype must be 0 (f64 fma), 1 (f32 fma), 2 (f32 rsqrt) or 3..6 (issue mixes)");
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return fail(MCH_ERR_CUDA, "mch_probe_fma: %s", cudaGetErrorString(e));
   return MCH_OK;

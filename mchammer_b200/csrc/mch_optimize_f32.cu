@@ -12,7 +12,7 @@ int launch_optimize_f32(bool io_f64, int mk, const OptArgs& a, int threads, int 
 // sweeps of 50 rows x 950 columns per CTA, optionally separated by __syncthreads().
 // ---------------------------------------------------------------------------------------
 template <int NTMAX>
-__global__ void __launch_bounds__(NTMAX, 1024 / NTMAX)
+__global__ void __launch_bounds__(NTMAX, (NTMAX == 64 ? 8 : 1024 / NTMAX))
 probe_sweep_kernel(int iters, int with_barrier, int nrows_real, int ncols, float* sink, int store) {
   extern __shared__ __align__(32) unsigned char smem[];
   const int N = 1000;
@@ -25,19 +25,20 @@ probe_sweep_kernel(int iters, int with_barrier, int nrows_real, int ncols, float
     X[n] = 0.013f * n + 0.5f * blockIdx.x; Y[n] = 7.0f - 0.009f * n; Z[n] = 0.003f * n * (n & 7);
   }
   constexpr bool kXF = (MCH_XF != 0);
+  constexpr bool kDup = kXF && (MCH_F32X2 != 0);
   const Centre<float> ctr{-5.7f, 21.7f, -7.8f};
   const int np = padded_rows(nrows_real);
   for (int i = threadIdx.x; i < np + 4; i += blockDim.x) {
-    Q[i] = i < nrows_real ? encode_row<float, kXF>(-3.0f - 0.11f * i, 20.0f + 0.07f * i, -9.0f + 0.05f * i, ctr)
-                          : padding_row<float, kXF>();
+    store_row<float, kDup>(Q, i, i < nrows_real ? encode_row<float, kXF>(-3.0f - 0.11f * i, 20.0f + 0.07f * i, -9.0f + 0.05f * i, ctr)
+                                                : padding_row<float, kXF>());
   }
   __syncthreads();
   const PairTerm<float, MU_3> term(3.0, 3);
   double total = 0.0;
   for (int it = 0; it < iters; ++it) {
     Cols cols{0, 0, 50, 50 + ncols};
-    if (store) total += pair_sweep<float, MU_3, false, true, kXF>(Q, np, X, Y, Z, colsum + (it & 1) * 1008, cols, term, ctr);
-    else total += pair_sweep<float, MU_3, false, false, kXF>(Q, np, X, Y, Z, (float*)nullptr, cols, term, ctr);
+    if (store) total += pair_sweep<float, MU_3, false, true, kXF, kDup>(Q, np, X, Y, Z, colsum + (it & 1) * 1008, cols, term, ctr);
+    else total += pair_sweep<float, MU_3, false, false, kXF, kDup>(Q, np, X, Y, Z, (float*)nullptr, cols, term, ctr);
     if (with_barrier) __syncthreads();
   }
   if (total == -1.2345) *sink = (float)total;
@@ -46,8 +47,11 @@ probe_sweep_kernel(int iters, int with_barrier, int nrows_real, int ncols, float
 int launch_probe_sweep(int blocks, int threads, int iters, int with_barrier, int nrows, int ncols, float* sink, cudaStream_t s) {
   const int store = with_barrier < 2 ? 1 : 0;  // with_barrier 2/3 = 0/1 without the column-sum stores
   with_barrier &= 1;
-  const int smem = (1008 * 3 + (store ? 2016 : 0)) * 4 + 64 * 16 + 256;
-  if (threads <= 128) {
+  const int smem = (1008 * 3 + (store ? 2016 : 0)) * 4 + 64 * 32 + 256;
+  if (threads <= 64) {
+    cudaFuncSetAttribute(probe_sweep_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    probe_sweep_kernel<64><<<blocks, threads, smem, s>>>(iters, with_barrier, nrows, ncols, sink, store);
+  } else if (threads <= 128) {
     cudaFuncSetAttribute(probe_sweep_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     probe_sweep_kernel<128><<<blocks, threads, smem, s>>>(iters, with_barrier, nrows, ncols, sink, store);
   } else {

@@ -10,7 +10,7 @@ from mchammer_b200 import native
 lib = native.lib()
 sink = torch.zeros(1, dtype=torch.float32, device="cuda")
 stream = torch.cuda.current_stream().cuda_stream
-configs = ((128, 8), (96, 10), (256, 4)) if "--all" in sys.argv else ((128, 8),)
+configs = ((128, 8), (64, 8), (96, 10), (256, 4)) if "--all" in sys.argv else ((128, 8),)
 for threads, per_sm in configs:
     for barrier in (0, 1):
         blocks, iters, rows, cols = 148 * per_sm, 2000, 50, 950

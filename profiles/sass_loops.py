@@ -17,7 +17,7 @@ for line in body.splitlines():
         ins.append((int(m.group(1), 16), m.group(2).strip()))
 addr_index = {a: i for i, (a, _) in enumerate(ins)}
 print(len(ins), "instructions")
-code = {"FADD": "a", "FMUL": "m", "FFMA": "f", "MUFU": "R", "LDS": "L", "STS": "S", "BRA": "B",
+code = {"FADD": "a", "FMUL": "m", "FFMA": "f", "FFMA2": "F", "FADD2": "A", "FMUL2": "M", "MUFU": "R", "LDS": "L", "STS": "S", "BRA": "B",
         "LDL": "!", "STL": "!", "DADD": "d", "DFMA": "d", "DMUL": "d", "BAR": "|"}
 for i, (a, text) in enumerate(ins):
     m = re.search(r"BRA(?:\.U)?\s+(?:!?U?P\d+,\s*)?0x([0-9a-f]+)", text)
