@@ -6,10 +6,15 @@
 //       pos[a] -= (step_size * v_s) * scale_s   for a in s                        (:84-104)
 //   if min distance < threshold / 2: one more step with step_size = -(step_size/2) (:264-276)
 //
-// Slot order: subunits contiguous, and inside each subunit the non-H atoms first, so the
-// heavy atoms of subunit s are the slot range [su_off[s], su_off[s] + n_heavy[s]).
-// The min-distance sweep gives every thread a heavy column atom j and walks the heavy
-// atoms of all EARLIER subunits (each cross pair once); rows are broadcast LDS.
+// Caller's slot order (the ABI): subunits contiguous, inside each subunit the non-H atoms
+// first (n_heavy[s] of them).  Inside the kernel the atoms are re-ordered once more: the
+// heavy atoms of ALL subunits first (grouped by subunit), then all H atoms, so that the
+// contact test works on one dense array q in [0, nh) in which the partners of column q --
+// the heavy atoms of all EARLIER subunits, each cross pair once -- are simply the rows
+// [0, hoff[subunit(q)]).  The triangle of (column, row) pairs is cut into blocks of
+// 128 columns x 32 rows that are dealt round-robin to the warps (equal cost per block, so
+// the triangle's imbalance disappears); a block entirely below every column's limit runs
+// without the per-pair "row belongs to an earlier subunit" predicate.  Rows are broadcast LDS.
 #pragma once
 
 #include "mch_device.cuh"
@@ -38,7 +43,7 @@ struct ColArgs {
   int trace_cap;
 };
 
-struct ColLayout { int x, y, z, suof, suoff, nheavy, bslot, csum, vec, wsum, total; };
+struct ColLayout { int x, y, z, suof, qatom, hoff, loff, bslot, csum, vec, wsum, total; };
 
 MCH_HD ColLayout col_layout(int N, int S, int B, int tsize) {
   ColLayout L;
@@ -47,9 +52,10 @@ MCH_HD ColLayout col_layout(int N, int S, int B, int tsize) {
   L.x = o; o += np * tsize;
   L.y = o; o += np * tsize;
   L.z = o; o += np * tsize;
-  L.suof = o; o += np * 4;
-  L.suoff = o; o += align_up(S + 1, 4) * 4;
-  L.nheavy = o; o += align_up(S, 4) * 4;
+  L.suof = o; o += np * 4;    // internal slot -> subunit
+  L.qatom = o; o += np * 4;   // internal slot -> atom id
+  L.hoff = o; o += align_up(S + 1, 4) * 4;  // heavy atoms before subunit s (internal slots of its heavy atoms)
+  L.loff = o; o += align_up(S + 1, 4) * 4;  // nh + H atoms before subunit s (internal slots of its H atoms)
   L.bslot = o; o += align_up(2 * B + 2, 4) * 4;
   o = align_up(o, 16);
   L.csum = o; o += S * 3 * 8;
@@ -74,19 +80,38 @@ mch_collapse_kernel(const __grid_constant__ ColArgs a) {
   T* Y = reinterpret_cast<T*>(smem + L.y);
   T* Z = reinterpret_cast<T*>(smem + L.z);
   int* suof = reinterpret_cast<int*>(smem + L.suof);
-  int* suoff = reinterpret_cast<int*>(smem + L.suoff);
-  int* nheavy = reinterpret_cast<int*>(smem + L.nheavy);
+  int* qatom = reinterpret_cast<int*>(smem + L.qatom);
+  int* hoff = reinterpret_cast<int*>(smem + L.hoff);
+  int* loff = reinterpret_cast<int*>(smem + L.loff);
   int* bslot = reinterpret_cast<int*>(smem + L.bslot);
   double* csum = reinterpret_cast<double*>(smem + L.csum);
   double* vec = reinterpret_cast<double*>(smem + L.vec);
   double* wsum = reinterpret_cast<double*>(smem + L.wsum);
 
   // ------------------------------------------------------------ prologue
-  for (int n = tid; n < N; n += nt) suof[a.perm[n]] = n;  // inverse permutation, temporarily
-  for (int s = tid; s <= S; s += nt) suoff[s] = a.su_off[s];
-  for (int s = tid; s < S; s += nt) nheavy[s] = a.n_heavy[s];
+  if (tid == 0) {  // prefix sums over subunits (once per molecule)
+    int h = 0, l = 0;
+    for (int s = 0; s < S; ++s) {
+      const int n = a.su_off[s + 1] - a.su_off[s], nh_s = a.n_heavy[s];
+      hoff[s] = h; loff[s] = l;
+      h += nh_s; l += n - nh_s;
+    }
+    hoff[S] = h; loff[S] = l;
+    for (int s = 0; s <= S; ++s) loff[s] += h;
+  }
   __syncthreads();
-  for (int k = tid; k < 2 * B; k += nt) bslot[k] = suof[a.bonds[k]];
+  const int nh = hoff[S];
+  int* inv = reinterpret_cast<int*>(X);  // atom id -> internal slot, N ints: borrows X (positions are loaded later)
+  for (int sidx = warp; sidx < S; sidx += nwarps) {
+    const int r0 = a.su_off[sidx], n = a.su_off[sidx + 1] - r0, nh_s = a.n_heavy[sidx];
+    for (int k = lane; k < n; k += 32) {
+      const int q = k < nh_s ? hoff[sidx] + k : loff[sidx] + (k - nh_s);
+      const int atom = a.perm[r0 + k];
+      qatom[q] = atom; suof[q] = sidx; inv[atom] = q;
+    }
+  }
+  __syncthreads();
+  for (int k = tid; k < 2 * B; k += nt) bslot[k] = inv[a.bonds[k]];
   __syncthreads();
   const long long in_base = (long long)c * a.pos_in_stride;
   double origin[3] = {0.0, 0.0, 0.0};
@@ -104,49 +129,63 @@ mch_collapse_kernel(const __grid_constant__ ColArgs a) {
     origin[0] /= N; origin[1] /= N; origin[2] /= N;
     __syncthreads();
   }
-  for (int n = tid; n < N; n += nt) {
-    const long long src = in_base + 3LL * a.perm[n];
-    X[n] = (T)(load_io<Tio>(a.pos_in, src + 0) - origin[0]);
-    Y[n] = (T)(load_io<Tio>(a.pos_in, src + 1) - origin[1]);
-    Z[n] = (T)(load_io<Tio>(a.pos_in, src + 2) - origin[2]);
+  for (int q = tid; q < N; q += nt) {
+    const long long src = in_base + 3LL * qatom[q];
+    X[q] = (T)(load_io<Tio>(a.pos_in, src + 0) - origin[0]);
+    Y[q] = (T)(load_io<Tio>(a.pos_in, src + 1) - origin[1]);
+    Z[q] = (T)(load_io<Tio>(a.pos_in, src + 2) - origin[2]);
   }
-  for (int s = warp; s < S; s += nwarps)
-    for (int n = suoff[s] + lane; n < suoff[s + 1]; n += 32) suof[n] = s;
   __syncthreads();
 
   // min over cross-subunit heavy pairs of r^2, as a distance (sqrt is monotone, so
   // min(dist) == sqrt(min r2) exactly)
+  constexpr int CT = 128, RB = 32;  // block = 4 column units x 32 rows
   auto min_cross_distance = [&]() -> double {
     T best = far_away<T>();
-    for (int base = 0; base < N; base += 4 * nt) {
+    const int n_ct = (nh + CT - 1) / CT;
+    int task = 0;
+    for (int ct = 0; ct < n_ct; ++ct) {
+      const int q0 = ct * CT;
+      const int q_last = min(q0 + CT, nh) - 1;
+      const int lim_lo = hoff[suof[q0]], lim_hi = hoff[suof[q_last]];  // rows of the first / last column
+      const int n_rb = (lim_hi + RB - 1) / RB;
+      // this warp's blocks of the column tile: task, task + nwarps, ...
+      int rb = (warp - task % nwarps + nwarps) % nwarps;
+      task += n_rb;
+      if (rb >= n_rb) continue;
       T xj[4], yj[4], zj[4], m[4];
       int lim[4];
-      int warp_lim = 0;
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
-        const int j = base + k * nt + tid;
-        bool live = j < N;
-        int s = live ? suof[j] : 0;
-        live = live && (j - suoff[s]) < nheavy[s];
-        lim[k] = live ? suoff[s] : 0;  // rows: all slots of earlier subunits
-        xj[k] = live ? X[j] : far_away<T>();
-        yj[k] = live ? Y[j] : far_away<T>();
-        zj[k] = live ? Z[j] : far_away<T>();
+        const int q = q0 + 32 * k + lane;
+        const bool live = q < nh;
+        lim[k] = live ? hoff[suof[q]] : 0;
+        xj[k] = live ? X[q] : far_away<T>();
+        yj[k] = live ? Y[q] : far_away<T>();
+        zj[k] = live ? Z[q] : far_away<T>();
         m[k] = far_away<T>();
-        warp_lim = lim[k] > warp_lim ? lim[k] : warp_lim;
       }
-      warp_lim = __reduce_max_sync(0xffffffffu, warp_lim);
-      for (int s = 0; s < S; ++s) {
-        const int r0 = suoff[s];
-        if (r0 >= warp_lim) break;
-        const int r1 = r0 + nheavy[s];
-        for (int i = r0; i < r1; ++i) {
-          const T xi = X[i], yi = Y[i], zi = Z[i];
+      for (; rb < n_rb; rb += nwarps) {
+        const int i0 = rb * RB, i1 = min(i0 + RB, lim_hi);
+        if (i1 <= lim_lo) {  // every row is a partner of every column of the tile
+#pragma unroll 4
+          for (int i = i0; i < i1; ++i) {
+            const T xi = X[i], yi = Y[i], zi = Z[i];
 #pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            const T dx = xj[k] - xi, dy = yj[k] - yi, dz = zj[k] - zi;
-            const T r2 = fma(dz, dz, fma(dy, dy, dx * dx));
-            m[k] = (i < lim[k] && r2 < m[k]) ? r2 : m[k];
+            for (int k = 0; k < 4; ++k) {
+              const T dx = xj[k] - xi, dy = yj[k] - yi, dz = zj[k] - zi;
+              m[k] = min(m[k], fma(dz, dz, fma(dy, dy, dx * dx)));
+            }
+          }
+        } else {
+          for (int i = i0; i < i1; ++i) {
+            const T xi = X[i], yi = Y[i], zi = Z[i];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              const T dx = xj[k] - xi, dy = yj[k] - yi, dz = zj[k] - zi;
+              const T r2 = fma(dz, dz, fma(dy, dy, dx * dx));
+              m[k] = (i < lim[k] && r2 < m[k]) ? r2 : m[k];
+            }
           }
         }
       }
@@ -165,7 +204,8 @@ mch_collapse_kernel(const __grid_constant__ ColArgs a) {
   auto do_step = [&](double step) {
     for (int s = warp; s < S; s += nwarps) {
       double sx = 0.0, sy = 0.0, sz = 0.0;
-      for (int n = suoff[s] + lane; n < suoff[s + 1]; n += 32) { sx += (double)X[n]; sy += (double)Y[n]; sz += (double)Z[n]; }
+      for (int n = hoff[s] + lane; n < hoff[s + 1]; n += 32) { sx += (double)X[n]; sy += (double)Y[n]; sz += (double)Z[n]; }
+      for (int n = loff[s] + lane; n < loff[s + 1]; n += 32) { sx += (double)X[n]; sy += (double)Y[n]; sz += (double)Z[n]; }
       sx = warp_sum(sx); sy = warp_sum(sy); sz = warp_sum(sz);
       if (lane == 0) { csum[3 * s] = sx; csum[3 * s + 1] = sy; csum[3 * s + 2] = sz; }
     }
@@ -176,7 +216,7 @@ mch_collapse_kernel(const __grid_constant__ ColArgs a) {
       tx = warp_sum(tx) / N; ty = warp_sum(ty) / N; tz = warp_sum(tz) / N;
       double big = 0.0;
       for (int s = lane; s < S; s += 32) {
-        const double n = (double)(suoff[s + 1] - suoff[s]);
+        const double n = (double)((hoff[s + 1] - hoff[s]) + (loff[s + 1] - loff[s]));
         const double vx = csum[3 * s] / n - tx, vy = csum[3 * s + 1] / n - ty, vz = csum[3 * s + 2] / n - tz;
         vec[3 * s] = vx; vec[3 * s + 1] = vy; vec[3 * s + 2] = vz;
         big = fmax(big, sqrt(vx * vx + vy * vy + vz * vz));
@@ -216,7 +256,7 @@ mch_collapse_kernel(const __grid_constant__ ColArgs a) {
     if (a.traj && step <= a.trace_cap) {
       const long long frame = ((long long)c * a.trace_cap + (step - 1)) * N * 3;
       for (int n = tid; n < N; n += nt) {
-        const long long dst = frame + 3LL * a.perm[n];
+        const long long dst = frame + 3LL * qatom[n];
         store_io<Tio>(a.traj, dst + 0, (double)X[n] + origin[0]);
         store_io<Tio>(a.traj, dst + 1, (double)Y[n] + origin[1]);
         store_io<Tio>(a.traj, dst + 2, (double)Z[n] + origin[2]);
@@ -242,7 +282,7 @@ mch_collapse_kernel(const __grid_constant__ ColArgs a) {
   }
   __syncthreads();
   for (int n = tid; n < N; n += nt) {
-    const long long dst = (long long)c * N * 3 + 3LL * a.perm[n];
+    const long long dst = (long long)c * N * 3 + 3LL * qatom[n];
     store_io<Tio>(a.pos_out, dst + 0, (double)X[n] + origin[0]);
     store_io<Tio>(a.pos_out, dst + 1, (double)Y[n] + origin[1]);
     store_io<Tio>(a.pos_out, dst + 2, (double)Z[n] + origin[2]);
