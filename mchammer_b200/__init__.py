@@ -8,7 +8,7 @@ calling a driver without CUDA or without the built library raises.
 
 from .collapser import CollapseBatchResult, Collapser
 from .elements import get_radius
-from .batch import BatchPlan, BatchResult, shard_bounds
+from .batch import BatchPlan, BatchResult, BatchTrajectory, shard_bounds
 from .optimizer import Optimizer
 from .primitives import (
     get_atom_distance,
@@ -42,6 +42,7 @@ __all__ = [
     # additions of this framework
     "BatchPlan",
     "BatchResult",
+    "BatchTrajectory",
     "CollapseBatchResult",
     "shard_bounds",
 ]

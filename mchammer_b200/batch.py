@@ -47,6 +47,26 @@ class BatchResult:
         return BatchResult(**fields)
 
 
+@dataclass
+class BatchTrajectory:
+    """Every step of ``C`` independent chains (host arrays; step 0 is the start geometry)."""
+
+    positions: np.ndarray | None     # [C,steps,N,3] io dtype (None when frames were not requested)
+    system_potential: np.ndarray     # [C,steps]
+    nonbonded_potential: np.ndarray  # [C,steps]
+    max_bond_distance: np.ndarray    # [C,steps]
+    passed: np.ndarray               # [C,steps] 1/0; -1 at step 0
+    bond_index: np.ndarray           # [C,steps] index into bond_pair_ids; -1 at step 0
+    final_positions: np.ndarray      # [C,N,3]
+    num_steps: int
+    seconds: float
+    d2h_bytes: int = 0
+    plan: object | None = None       # keeps the pinned host buffers alive when the caller dropped the plan
+
+    def __len__(self) -> int:
+        return int(self.system_potential.shape[0])
+
+
 def unpack_info(info: np.ndarray):
     """Split trace words: bond | passed << 16 | kind << 17 | moved subunit << 18 (-1: no move)."""
     info = np.asarray(info, dtype=np.int64)
@@ -266,6 +286,96 @@ class BatchPlan:
                 torch.cuda.current_stream(sh.device).wait_stream(st)
         return (self.h_pos_out.numel() * self.h_pos_out.element_size() + self.h_f64.numel() * 8
                 + self.h_i32.numel() * 4 + self.h_pairs.numel() * 8)
+
+    def run_trajectories(self, seeds: Sequence[int] | None = None, positions=None,
+                         rng_words: np.ndarray | None = None, want_positions: bool = True,
+                         slice_bytes: int = 1 << 30, pin_limit_bytes: int = 8 << 30) -> BatchTrajectory:
+        """Like ``run`` but keeps every step: per-step potentials / accept flags and, if
+        ``want_positions``, the frames ``[C, num_steps, N, 3]`` (reference ``get_trajectory``,
+        results.py:149-152, for a whole batch).
+
+        Frames are the only bulky output of the path (``num_steps * N * 3`` values per chain),
+        so they are streamed: every device works through its chains in slices of at most
+        ``slice_bytes`` of frames, two device frame buffers alternate on two streams, and the
+        device->host copy of one slice runs under the kernel of the next.  The host array is
+        pinned when it is at most ``pin_limit_bytes`` (asynchronous copies), pageable above; like
+        the buffers of ``run`` it belongs to the plan and is overwritten by the next call.
+        """
+        torch = self._torch
+        start = time.perf_counter()
+        self.stage_inputs(seeds, positions, rng_words)
+        c, n, steps = self.n_chains, self.topo.n_atoms, self.num_steps
+        tdtype = self.h_pos_in.dtype
+        item = self.h_pos_in.element_size()
+        frame_bytes = steps * n * 3 * item
+
+        def host(name, shape, dtype, nbytes):
+            # host buffers are kept with the plan (pinning gigabytes costs more than the copy)
+            cache = self.__dict__.setdefault("_traj_host", {})
+            if name not in cache:
+                t = torch.empty(shape, dtype=dtype)
+                cache[name] = t.pin_memory() if nbytes <= pin_limit_bytes else t
+            return cache[name]
+
+        h_traj = host("frames", (c, steps, n, 3), tdtype, c * frame_bytes) if want_positions else None
+        h_trace = host("trace", (c, steps, 3), torch.float64, 0)
+        h_info = host("info", (c, steps), torch.int32, 0)
+        for sh in self.shards:
+            with torch.cuda.device(sh.device):
+                main = torch.cuda.current_stream(sh.device)
+                per = max(1, min(sh.count, int(slice_bytes // max(frame_bytes, 1)) if want_positions else sh.count))
+                while len(sh.streams) < 2:
+                    sh.streams.append(torch.cuda.Stream(device=sh.device))
+                lanes = sh.streams[:2]
+                f64 = dict(dtype=torch.float64, device=sh.device)
+                bufs = [dict(
+                    traj=torch.empty((per, steps, n, 3), dtype=tdtype, device=sh.device) if want_positions else None,
+                    trace=torch.empty((per, steps, 3), **f64),
+                    info=torch.empty((per, steps), dtype=torch.int32, device=sh.device),
+                ) for _ in lanes]
+                if not self.per_chain_positions:
+                    sh.pos_in.copy_(self.h_pos_in, non_blocking=True)
+                for st in lanes:
+                    st.wait_stream(main)
+                for k, lo in enumerate(range(0, sh.count, per)):
+                    hi = min(lo + per, sh.count)
+                    m = hi - lo
+                    buf = bufs[k % 2]
+                    with torch.cuda.stream(lanes[k % 2]):
+                        g_lo, g_hi = sh.lo + lo, sh.lo + hi
+                        if self.per_chain_positions:
+                            sh.pos_in[lo:hi].copy_(self.h_pos_in[g_lo:g_hi], non_blocking=True)
+                            pos = sh.pos_in[lo:hi]
+                        else:
+                            pos = sh.pos_in
+                        sh.rng[lo:hi].copy_(self.h_rng[g_lo:g_hi], non_blocking=True)
+                        o = sh.out_slice(lo, hi)
+                        o.trace_potentials, o.trace_info = buf["trace"][:m], buf["info"][:m]
+                        o.trajectory = buf["traj"][:m] if want_positions else None
+                        engine.optimize_on_device(
+                            sh.dtopo, pos, m, sh.rng[lo:hi], self.params, steps, self.precision,
+                            threads_per_chain=self.threads_per_chain, out=o,
+                        )
+                        if want_positions:
+                            h_traj[g_lo:g_hi].copy_(o.trajectory, non_blocking=True)
+                        h_trace[g_lo:g_hi].copy_(o.trace_potentials, non_blocking=True)
+                        h_info[g_lo:g_hi].copy_(o.trace_info, non_blocking=True)
+                        self.h_pos_out[g_lo:g_hi].copy_(o.positions, non_blocking=True)
+        for sh in self.shards:
+            for st in sh.streams[:2]:
+                st.synchronize()
+                torch.cuda.current_stream(sh.device).wait_stream(st)
+        trace = h_trace.numpy()
+        bond, passed, _, _ = unpack_info(h_info.numpy())
+        d2h = ((c * frame_bytes if want_positions else 0) + h_trace.numel() * 8 + h_info.numel() * 4
+               + self.h_pos_out.numel() * item)
+        return BatchTrajectory(
+            positions=h_traj.numpy() if want_positions else None,
+            system_potential=trace[:, :, 0], nonbonded_potential=trace[:, :, 1],
+            max_bond_distance=trace[:, :, 2], passed=passed, bond_index=bond,
+            final_positions=self.h_pos_out.numpy().copy(), num_steps=steps,
+            seconds=time.perf_counter() - start, d2h_bytes=d2h,
+        )
 
     def run(self, seeds: Sequence[int] | None = None, positions=None,
             rng_words: np.ndarray | None = None) -> BatchResult:

@@ -16,7 +16,7 @@ from typing import Sequence
 import numpy as np
 
 from . import engine, native, rngstate
-from .batch import BatchPlan, BatchResult, shard_bounds, unpack_info
+from .batch import BatchPlan, BatchResult, BatchTrajectory, shard_bounds, unpack_info
 from .lowering import lower_topology
 from .records import MCStepResult, Result
 from .structure import Molecule
@@ -294,3 +294,80 @@ class Optimizer:
             per_chain_positions=positions is not None, threads_per_chain=threads_per_chain,
         )
         return plan.run(seeds=seeds, positions=positions).copy()
+
+    def get_trajectories_batch(
+        self,
+        mol: Molecule,
+        bond_pair_ids,
+        subunits: dict,
+        seeds: Sequence[int],
+        positions: np.ndarray | None = None,
+        devices: Sequence[int] | None = None,
+        io_dtype=np.float64,
+        want_positions: bool = True,
+        slice_bytes: int = 1 << 30,
+    ) -> BatchTrajectory:
+        """Every step of many independent chains (NEW): what ``get_trajectory`` records, for
+        chain ``c`` = ``Optimizer(..., random_seed=seeds[c])`` on ``positions[c]`` (or ``mol``).
+
+        Returns per-step potentials, accept flags, bond choices and -- unless
+        ``want_positions=False`` -- the frames ``[C, num_steps, N, 3]`` in ``io_dtype``, streamed
+        off the device slice by slice (see :meth:`BatchPlan.run_trajectories`).
+        ``trajectory_result(traj, c, bond_pair_ids, subunits)`` rebuilds the reference-style
+        :class:`Result` (records + log text) of one chain.
+        """
+        native.require_cuda()
+        seeds = [int(s) for s in seeds]
+        if positions is not None:
+            positions = np.ascontiguousarray(positions, dtype=io_dtype)
+            if positions.shape != (len(seeds), mol.get_num_atoms(), 3):
+                raise ValueError("positions must have shape [len(seeds), n_atoms, 3]")
+        plan = self.prepare_batch(
+            mol, bond_pair_ids, subunits, len(seeds), devices, io_dtype,
+            per_chain_positions=positions is not None,
+        )
+        # the plan (and the pinned buffers the arrays live in) is owned by the returned object
+        traj = plan.run_trajectories(seeds=seeds, positions=positions, want_positions=want_positions,
+                                     slice_bytes=slice_bytes)
+        traj.plan = plan
+        return traj
+
+    def trajectory_result(self, traj: BatchTrajectory, chain: int, bond_pair_ids, subunits: dict) -> Result:
+        """The reference-style ``Result`` (step records and the full log text, optimizer.py:308-390)
+        of chain ``chain`` of a :class:`BatchTrajectory`."""
+        result = Result(start_time=time.time())
+        result.update_log(self._output_top_lines())
+        result.update_log(f"There are {len(bond_pair_ids)} bonds to optimize.\n")
+        result.update_log(
+            f"There are {len(subunits)} sub units with N atoms:\n"
+            f"{[len(subunits[i]) for i in subunits]}\n"
+        )
+        rule = "=" * 52 + "\n"
+        result.update_log(rule + " " * 17 + "Running optimisation!" + " " * 14 + "\n" + rule + "\n")
+        result.update_log("step system_potential nonbond_potential max_dist opt_bbs updated?\n")
+        bond_table = np.asarray(bond_pair_ids)
+        for step in range(traj.num_steps):
+            u = float(traj.system_potential[chain, step])
+            unb = float(traj.nonbonded_potential[chain, step])
+            far = float(traj.max_bond_distance[chain, step])
+            if traj.passed[chain, step] < 0:
+                flag, row = None, None
+            else:
+                flag, row = bool(traj.passed[chain, step]), bond_table[int(traj.bond_index[chain, step])]
+            frame = None if traj.positions is None else np.array(traj.positions[chain, step], dtype=np.float64)
+            result.add_step_result(
+                MCStepResult(
+                    step=step, position_matrix=frame, passed=flag, system_potential=u,
+                    nonbonded_potential=unb, max_bond_distance=far,
+                    log=self._step_log(step, u, unb, far, row, flag),
+                )
+            )
+        num_passed = result.get_number_passed()
+        result.update_log(
+            "\n============================================\n"
+            "Optimisation done:\n"
+            f"{num_passed} steps passed: {(num_passed / self._num_steps) * 100}%\n"
+            f"Total optimisation time: {round(traj.seconds, 4)}s\n"
+            "============================================\n"
+        )
+        return result

@@ -311,6 +311,44 @@ def test_fp32_mode_other_exponents(case):
     assert rel_close(u, g["system_potential"][:prefix], RTOL32)
 
 
+def test_batch_trajectories_match_reference_and_single_chain():
+    # chain 0 of a batched trajectory = the reference's seeded get_trajectory (golden, seed 1000);
+    # chain 1 (seed 7) = the other golden of the same molecule; streamed in slices of ONE chain
+    g, g7 = load_golden("poc_graph_seed1000"), load_golden("poc_graph_seed7")
+    mol, bonds, subunits = golden_molecule(g), golden_bonds(g), golden_subunits(g)
+    opt = golden_optimizer(g)
+    n, steps = mol.get_num_atoms(), int(g["num_steps"])
+    frame_bytes = steps * n * 3 * 8
+    traj = opt.get_trajectories_batch(mol, bonds, subunits, seeds=[1000, 7, 1000],
+                                      slice_bytes=frame_bytes, devices=[0, 0])
+    assert len(traj) == 3 and traj.positions.shape == (3, steps, n, 3)
+    for c, want in ((0, g), (1, g7), (2, g)):
+        assert np.array_equal(traj.passed[c], want["passed"]), "accept/reject sequence differs from the reference"
+        assert rel_close(traj.system_potential[c], want["system_potential"], RTOL64)
+        assert rel_close(traj.nonbonded_potential[c], want["nonbonded_potential"], RTOL64)
+        assert rel_close(traj.max_bond_distance[c], want["max_bond_distance"], RTOL64)
+        assert np.allclose(traj.final_positions[c], want["final_positions"], rtol=RTOL64, atol=1e-9)
+        assert np.allclose(traj.positions[c, -1], want["final_positions"], rtol=RTOL64, atol=1e-9)
+        if "positions" in want.files:
+            assert np.allclose(traj.positions[c], want["positions"], rtol=RTOL64, atol=1e-9)
+    assert np.array_equal(traj.positions[0], traj.positions[2])
+    # the rebuilt Result carries the reference's log text
+    result = opt.trajectory_result(traj, 0, bonds, subunits)
+    assert result.get_step_count() == steps - 1
+    assert result.get_number_passed() == int(g["number_passed"])
+    got_lines, want_lines = result.get_log().splitlines(), str(g["log"]).splitlines()
+    assert len(got_lines) == len(want_lines)
+    for got, want in zip(got_lines, want_lines):
+        gt, wt = got.split(), want.split()
+        if len(wt) >= 6 and wt[0].isdigit():
+            assert gt[0] == wt[0] and gt[4:] == wt[4:], (got, want)
+    # without frames: same traces, nothing bulky comes back
+    lean = opt.get_trajectories_batch(mol, bonds, subunits, seeds=[1000, 7], want_positions=False)
+    assert lean.positions is None
+    assert np.array_equal(lean.system_potential, traj.system_potential[:2])
+    assert lean.d2h_bytes < traj.d2h_bytes / 50
+
+
 def test_batch_io_float32_and_two_shards_on_one_device():
     mol, long_bonds, subunits = synthetic.cube_cage(atoms_per_subunit=10, seed=4, spread=6.0)
     seeds = list(range(40, 47))
