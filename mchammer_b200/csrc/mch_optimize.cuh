@@ -100,7 +100,7 @@ MCH_HD OptLayout opt_layout(int N, int S, int B, int max_su, int tsize, int defe
   L.colsum = o; L.colsum_stride = np * (tsize < 4 ? 4 : tsize);
   o += (defer ? 2 : 1) * L.colsum_stride;  // double buffered when control work is deferred
   o = align_up(o, 32);
-  L.rows = o; o += (max_su + 4) * row_bytes(tsize);  // + far-away padding row + prefetch overrun
+  L.rows = o; o += (max_su + kRowSlack) * row_bytes(tsize);  // + far-away padding row + prefetch overrun
   o = align_up(o, 16);
   L.E = o; o += S * S * 8;
   L.erow = o; o += S * 8;
@@ -225,6 +225,7 @@ mch_optimize_kernel(const __grid_constant__ OptArgs a) {
   constexpr bool kFast = sizeof(T) == 4;  // fp32 mode: cheaper centroid bookkeeping
   constexpr bool kXF = kFast && (MCH_XF != 0);  // expanded-form squared distances (mch_device.cuh)
   constexpr bool kDup = kXF && (MCH_F32X2 != 0);  // duplicated row buffer, packed-instruction tile
+  constexpr int kRot3 = !(kDup && (MCH_X2_ROT3 != 0)) ? 0 : (NTMAX <= 64 ? 2 : 1);  // 2: deep row prefetch (128 registers)
   const bool kDefer = a.defer != 0;  // host policy: off when the second buffer would cost a resident chain
   Pcg64 rng;  // loaded after step 0 (nothing of the control state is live across the step-0 sweeps)
   rng.hi = rng.lo = rng.inc_hi = rng.inc_lo = 0ULL; rng.has32 = rng.half = 0u;
@@ -258,7 +259,7 @@ mch_optimize_kernel(const __grid_constant__ OptArgs a) {
   // warp 0 only.  Expanded encoding: relative to the centroid of the displaced subunit, which
   // is also published for the column side.  Returns the padded count.
   auto fill_rows = [&](int s, T dx, T dy, T dz) {
-    const int r0 = suoff[s], n = suoff[s + 1] - r0, np = padded_rows(n);
+    const int r0 = suoff[s], n = suoff[s + 1] - r0, np = kRot3 ? padded_rows3(n) : padded_rows(n);
     Centre<T> ctr{(T)0, (T)0, (T)0};
     if (kXF) {
       ctr.x = (T)(csum[3 * s] * invn[s]) - dx;
@@ -418,7 +419,7 @@ mch_optimize_kernel(const __grid_constant__ OptArgs a) {
     {
       Cols cross{ctl->c0, ctl->g0, ctl->g1, ctl->c1};
       const Centre<T> ctr{(T)ctl->cx, (T)ctl->cy, (T)ctl->cz};
-      (void)pair_sweep<T, MUK, false, true, kXF, kDup>(Q, ctl->nrows, X, Y, Z, colsum, cross, term, ctr);
+      (void)pair_sweep<T, MUK, false, true, kXF, kDup, kRot3>(Q, ctl->nrows, X, Y, Z, colsum, cross, term, ctr);
       const int r0 = suoff[s], nrows = suoff[s + 1] - r0;
       Cols own{r0, r0 + nrows, r0 + nrows, r0 + nrows};
       double tri = pair_sweep<T, MUK, true, false, kXF, kDup>(Q, nrows, X, Y, Z, (T*)nullptr, own, term, ctr);
@@ -493,7 +494,7 @@ mch_optimize_kernel(const __grid_constant__ OptArgs a) {
       // warp 0 spends roughly the time of 100 rows x 32 columns on the deferred control work:
       // one pair of column units less for subunits of up to ~50 atoms, nothing for large ones
       const int handicap = kDefer ? min(1, 50 / ctl->nrows) : 0;
-      double part = pair_sweep<T, MUK, false, true, kXF, kDup>(Q, ctl->nrows, X, Y, Z, colsum + ctl->buf * colsum_stride, others, term, ctr, handicap);
+      double part = pair_sweep<T, MUK, false, true, kXF, kDup, kRot3>(Q, ctl->nrows, X, Y, Z, colsum + ctl->buf * colsum_stride, others, term, ctr, handicap);
       part = warp_sum(part);
       if (lane == 0) wsum[warp] = part;
     }

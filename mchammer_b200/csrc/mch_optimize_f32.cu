@@ -26,9 +26,10 @@ probe_sweep_kernel(int iters, int with_barrier, int nrows_real, int ncols, float
   }
   constexpr bool kXF = (MCH_XF != 0);
   constexpr bool kDup = kXF && (MCH_F32X2 != 0);
+  constexpr int kRot3 = !(kDup && (MCH_X2_ROT3 != 0)) ? 0 : (NTMAX <= 64 ? 2 : 1);
   const Centre<float> ctr{-5.7f, 21.7f, -7.8f};
-  const int np = padded_rows(nrows_real);
-  for (int i = threadIdx.x; i < np + 4; i += blockDim.x) {
+  const int np = kRot3 ? padded_rows3(nrows_real) : padded_rows(nrows_real);
+  for (int i = threadIdx.x; i < np + 3; i += blockDim.x) {
     store_row<float, kDup>(Q, i, i < nrows_real ? encode_row<float, kXF>(-3.0f - 0.11f * i, 20.0f + 0.07f * i, -9.0f + 0.05f * i, ctr)
                                                 : padding_row<float, kXF>());
   }
@@ -37,8 +38,8 @@ probe_sweep_kernel(int iters, int with_barrier, int nrows_real, int ncols, float
   double total = 0.0;
   for (int it = 0; it < iters; ++it) {
     Cols cols{0, 0, 50, 50 + ncols};
-    if (store) total += pair_sweep<float, MU_3, false, true, kXF, kDup>(Q, np, X, Y, Z, colsum + (it & 1) * 1008, cols, term, ctr);
-    else total += pair_sweep<float, MU_3, false, false, kXF, kDup>(Q, np, X, Y, Z, (float*)nullptr, cols, term, ctr);
+    if (store) total += pair_sweep<float, MU_3, false, true, kXF, kDup, kRot3>(Q, np, X, Y, Z, colsum + (it & 1) * 1008, cols, term, ctr);
+    else total += pair_sweep<float, MU_3, false, false, kXF, kDup, kRot3>(Q, np, X, Y, Z, (float*)nullptr, cols, term, ctr);
     if (with_barrier) __syncthreads();
   }
   if (total == -1.2345) *sink = (float)total;
@@ -47,7 +48,7 @@ probe_sweep_kernel(int iters, int with_barrier, int nrows_real, int ncols, float
 int launch_probe_sweep(int blocks, int threads, int iters, int with_barrier, int nrows, int ncols, float* sink, cudaStream_t s) {
   const int store = with_barrier < 2 ? 1 : 0;  // with_barrier 2/3 = 0/1 without the column-sum stores
   with_barrier &= 1;
-  const int smem = (1008 * 3 + (store ? 2016 : 0)) * 4 + 64 * 32 + 256;
+  const int smem = (1008 * 3 + (store ? 2016 : 0)) * 4 + 72 * 32 + 256;
   if (threads <= 64) {
     cudaFuncSetAttribute(probe_sweep_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     probe_sweep_kernel<64><<<blocks, threads, smem, s>>>(iters, with_barrier, nrows, ncols, sink, store);
