@@ -522,6 +522,30 @@ def test_collapser_batch_with_hydrogens_against_oracle():
     del rng
 
 
+@pytest.mark.parametrize("threads", [0, 96, 256])
+def test_collapser_full_size_cage_block_dealing(threads):
+    # 1000 atoms, ~700 heavy: six 128-column tiles x up to 21 row blocks of the contact-test
+    # triangle, dealt over 4 / 3 / 8 warps -- steps, contact distance and geometry vs the oracle
+    from mchammer_b200 import engine
+    from mchammer_b200.lowering import lower_topology
+    import torch
+
+    mol, long_bonds, subunits = synthetic.cube_cage(h_fraction=0.3)
+    base = mol.get_position_matrix()
+    elements = [a.get_element_string() for a in mol.get_atoms()]
+    is_h = [e == "H" for e in elements]
+    topo = lower_topology(mol.get_num_atoms(), long_bonds, subunits, elements=elements, require_bond_subunits=False)
+    dtopo = engine.upload_topology(topo, 0)
+    positions = np.stack([base, base * 1.03])
+    out = engine.collapse_on_device(dtopo, torch.from_numpy(positions).cuda(), 2, 0.02, 1.5, True, "fp64",
+                                    threads_per_mol=threads)
+    for m in range(2):
+        want = orc.collapser_run(positions[m], is_h, long_bonds, subunits, 0.02, 1.5, True)
+        assert int(out.steps_run[m].item()) == want.steps_run
+        assert rel_close(out.min_distance[m].item(), want.min_distance, RTOL64)
+        assert np.allclose(out.positions[m].cpu().numpy(), want.final_positions, rtol=RTOL64, atol=1e-9)
+
+
 def test_collapser_never_touching_raises():
     pos = np.array([[0.0, 0, 0], [1.5, 0, 0], [3.0, 0, 0]])
     mol = mch.Molecule(atoms=[mch.Atom(i, "C") for i in range(3)], bonds=[], position_matrix=pos)
