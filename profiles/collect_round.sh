@@ -17,6 +17,7 @@ python profiles/latency.py > $O/${R}_latency.txt 2>&1
 python profiles/small_batch.py > $O/${R}_small_batch.txt 2>&1
 python profiles/phase_times.py > $O/${R}_phase_times.txt 2>&1
 python profiles/collapse_batch.py > $O/${R}_collapse_batch.txt 2>&1
+python profiles/potential_batch.py > $O/${R}_potential_batch.txt 2>&1
 python profiles/trajectory_stream.py > $O/${R}_trajectory_stream.txt 2>&1
 # profiler passes: the same command exited 0 above without ncu
 if python bench.py --steps 2 --warmup 1 --no-cpu-baseline > $O/${R}_bench_short.json 2>> $O/${R}_bench.err; then
