@@ -148,9 +148,9 @@ int mch_pcg64_stream_check(uint64_t* rng_state /* [6] in/out */, int rounds, uin
 
 /* Arithmetic-pipe probe for the roofline denominators: every thread runs `iters` rounds of
  * 8 independent FMAs in `dtype` (0 = f64, 1 = f32; 2 = 8 f32 MUFU.RSQ instead);
- * 2*8*iters*blocks*threads flops per launch.  dtype 3..6 are issue-mix probes of 8 (mode 6:
+ * 2*8*iters*blocks*threads flops per launch.  dtype 3..7 are issue-mix probes of 8 (mode 6:
  * 14) instructions per round -- 3: 8 FFMA2, 4: 6 FFMA2 + 2 MUFU.RSQ, 5: 6 FFMA + 2 MUFU.RSQ,
- * 6: 12 FFMA + 2 MUFU.RSQ -- read by profiles/probe_mix.py. */
+ * 6: 12 FFMA + 2 MUFU.RSQ, 7: mode 4 with one broadcast LDS.128 -- read by profiles/probe_mix.py. */
 int mch_probe_fma(int dtype, int blocks, int threads, int iters, float* sink /* [dev] [1] */,
                   void* stream);
 

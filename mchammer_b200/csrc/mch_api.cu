@@ -122,6 +122,7 @@ __global__ void probe_rsqrt_kernel(int iters, float* sink) {
 // Issue-mix probes (profiles/probe_mix.py): 8 independent instructions per iteration.
 //   MODE 3: 8 FFMA2        MODE 4: 6 FFMA2 + 2 MUFU.RSQ
 //   MODE 5: 6 FFMA + 2 MUFU.RSQ     MODE 6: 12 FFMA + 2 MUFU.RSQ (the scalar work of mode 4)
+//   MODE 7: mode 4 + 1 broadcast LDS.128 feeding the FFMA2s
 template <int MODE>
 __global__ void probe_mix_kernel(int iters, float* sink) {
   const float t = 1e-3f * threadIdx.x;
@@ -133,10 +134,20 @@ __global__ void probe_mix_kernel(int iters, float* sink) {
 #pragma unroll
   for (int k = 0; k < 12; ++k) f[k] = t + 0.5f * k;
   f32x2 q0 = pack2(t, 1.f), q1 = pack2(t, 2.f);
+  __shared__ ulonglong2 rowbuf[64];
+  if (MODE == 7) {
+    if (threadIdx.x < 64) rowbuf[threadIdx.x] = make_ulonglong2(m2, c2);
+    __syncthreads();
+  }
   for (int i = 0; i < iters; ++i) {
     if (MODE == 3 || MODE == 4) {
 #pragma unroll
       for (int k = 0; k < 6; ++k) p[k] = fma2(p[k], m2, c2);
+    }
+    if (MODE == 7) {  // mode 4 with its operands broadcast from shared memory (one LDS.128 per round)
+      const ulonglong2 q = rowbuf[i & 63];
+#pragma unroll
+      for (int k = 0; k < 6; ++k) p[k] = fma2(p[k], q.x, q.y);
     }
     if (MODE == 3) { q0 = fma2(q0, m2, c2); q1 = fma2(q1, m2, c2); }
     if (MODE == 5 || MODE == 6) {
@@ -375,7 +386,8 @@ int mch_probe_fma(int dtype, int blocks, int threads, int iters, float* sink, vo
   else if (dtype == 4) probe_mix_kernel<4><<<blocks, threads, 0, s>>>(iters, sink);
   else if (dtype == 5) probe_mix_kernel<5><<<blocks, threads, 0, s>>>(iters, sink);
   else if (dtype == 6) probe_mix_kernel<6><<<blocks, threads, 0, s>>>(iters, sink);
-  else return fail(MCH_ERR_INVALID, "mch_probe_fma: dtype must be 0 (f64 fma), 1 (f32 fma), 2 (f32 rsqrt) or 3..6 (issue mixes)");
+  else if (dtype == 7) probe_mix_kernel<7><<<blocks, threads, 0, s>>>(iters, sink);
+  else return fail(MCH_ERR_INVALID, "mch_probe_fma: dtype must be 0 (f64 fma), 1 (f32 fma), 2 (f32 rsqrt) or 3..7 (issue mixes)");
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return fail(MCH_ERR_CUDA, "mch_probe_fma: %s", cudaGetErrorString(e));
   return MCH_OK;

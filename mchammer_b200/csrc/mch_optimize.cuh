@@ -224,8 +224,8 @@ mch_optimize_kernel(const __grid_constant__ OptArgs a) {
   // (uniform across the 32 lanes of warp 0; other warps never read it)
   constexpr bool kFast = sizeof(T) == 4;  // fp32 mode: cheaper centroid bookkeeping
   constexpr bool kXF = kFast && (MCH_XF != 0);  // expanded-form squared distances (mch_device.cuh)
-  constexpr bool kDup = kXF && (MCH_F32X2 != 0);  // duplicated row buffer, packed-instruction tile
-  constexpr int kRot3 = !(kDup && (MCH_X2_ROT3 != 0)) ? 0 : (NTMAX <= 64 ? 2 : 1);  // 2: deep row prefetch (128 registers)
+  constexpr bool kX2 = kXF && (MCH_F32X2 != 0);  // packed-instruction tile
+  constexpr int kRot3 = !(kX2 && (MCH_X2_ROT3 != 0)) ? 0 : (NTMAX <= 64 ? 2 : 1);  // 2: deep row prefetch (128 registers)
   const bool kDefer = a.defer != 0;  // host policy: off when the second buffer would cost a resident chain
   Pcg64 rng;  // loaded after step 0 (nothing of the control state is live across the step-0 sweeps)
   rng.hi = rng.lo = rng.inc_hi = rng.inc_lo = 0ULL; rng.has32 = rng.half = 0u;
@@ -268,8 +268,8 @@ mch_optimize_kernel(const __grid_constant__ OptArgs a) {
       if (lane == 0) { ctl->cx = (double)ctr.x; ctl->cy = (double)ctr.y; ctl->cz = (double)ctr.z; }
     }
     for (int i = lane; i < np; i += 32) {
-      store_row<T, kDup>(Q, i, i < n ? encode_row<T, kXF>(X[r0 + i] - dx, Y[r0 + i] - dy, Z[r0 + i] - dz, ctr)
-                                     : padding_row<T, kXF>());
+      Q[i] = i < n ? encode_row<T, kXF>(X[r0 + i] - dx, Y[r0 + i] - dy, Z[r0 + i] - dz, ctr)
+                   : padding_row<T, kXF>();
     }
     return np;
   };
@@ -419,10 +419,10 @@ mch_optimize_kernel(const __grid_constant__ OptArgs a) {
     {
       Cols cross{ctl->c0, ctl->g0, ctl->g1, ctl->c1};
       const Centre<T> ctr{(T)ctl->cx, (T)ctl->cy, (T)ctl->cz};
-      (void)pair_sweep<T, MUK, false, true, kXF, kDup, kRot3>(Q, ctl->nrows, X, Y, Z, colsum, cross, term, ctr);
+      (void)pair_sweep<T, MUK, false, true, kXF, kX2, kRot3>(Q, ctl->nrows, X, Y, Z, colsum, cross, term, ctr);
       const int r0 = suoff[s], nrows = suoff[s + 1] - r0;
       Cols own{r0, r0 + nrows, r0 + nrows, r0 + nrows};
-      double tri = pair_sweep<T, MUK, true, false, kXF, kDup>(Q, nrows, X, Y, Z, (T*)nullptr, own, term, ctr);
+      double tri = pair_sweep<T, MUK, true, false, kXF, kX2>(Q, nrows, X, Y, Z, (T*)nullptr, own, term, ctr);
       tri = warp_sum(tri);
       if (lane == 0) wsum[32 + warp] = tri;
     }
@@ -494,7 +494,7 @@ mch_optimize_kernel(const __grid_constant__ OptArgs a) {
       // warp 0 spends roughly the time of 100 rows x 32 columns on the deferred control work:
       // one pair of column units less for subunits of up to ~50 atoms, nothing for large ones
       const int handicap = kDefer ? min(1, 50 / ctl->nrows) : 0;
-      double part = pair_sweep<T, MUK, false, true, kXF, kDup, kRot3>(Q, ctl->nrows, X, Y, Z, colsum + ctl->buf * colsum_stride, others, term, ctr, handicap);
+      double part = pair_sweep<T, MUK, false, true, kXF, kX2, kRot3>(Q, ctl->nrows, X, Y, Z, colsum + ctl->buf * colsum_stride, others, term, ctr, handicap);
       part = warp_sum(part);
       if (lane == 0) wsum[warp] = part;
     }

@@ -25,21 +25,21 @@ probe_sweep_kernel(int iters, int with_barrier, int nrows_real, int ncols, float
     X[n] = 0.013f * n + 0.5f * blockIdx.x; Y[n] = 7.0f - 0.009f * n; Z[n] = 0.003f * n * (n & 7);
   }
   constexpr bool kXF = (MCH_XF != 0);
-  constexpr bool kDup = kXF && (MCH_F32X2 != 0);
-  constexpr int kRot3 = !(kDup && (MCH_X2_ROT3 != 0)) ? 0 : (NTMAX <= 64 ? 2 : 1);
+  constexpr bool kX2 = kXF && (MCH_F32X2 != 0);
+  constexpr int kRot3 = !(kX2 && (MCH_X2_ROT3 != 0)) ? 0 : (NTMAX <= 64 ? 2 : 1);
   const Centre<float> ctr{-5.7f, 21.7f, -7.8f};
   const int np = kRot3 ? padded_rows3(nrows_real) : padded_rows(nrows_real);
   for (int i = threadIdx.x; i < np + 3; i += blockDim.x) {
-    store_row<float, kDup>(Q, i, i < nrows_real ? encode_row<float, kXF>(-3.0f - 0.11f * i, 20.0f + 0.07f * i, -9.0f + 0.05f * i, ctr)
-                                                : padding_row<float, kXF>());
+    Q[i] = i < nrows_real ? encode_row<float, kXF>(-3.0f - 0.11f * i, 20.0f + 0.07f * i, -9.0f + 0.05f * i, ctr)
+                          : padding_row<float, kXF>();
   }
   __syncthreads();
   const PairTerm<float, MU_3> term(3.0, 3);
   double total = 0.0;
   for (int it = 0; it < iters; ++it) {
     Cols cols{0, 0, 50, 50 + ncols};
-    if (store) total += pair_sweep<float, MU_3, false, true, kXF, kDup, kRot3>(Q, np, X, Y, Z, colsum + (it & 1) * 1008, cols, term, ctr);
-    else total += pair_sweep<float, MU_3, false, false, kXF, kDup, kRot3>(Q, np, X, Y, Z, (float*)nullptr, cols, term, ctr);
+    if (store) total += pair_sweep<float, MU_3, false, true, kXF, kX2, kRot3>(Q, np, X, Y, Z, colsum + (it & 1) * 1008, cols, term, ctr);
+    else total += pair_sweep<float, MU_3, false, false, kXF, kX2, kRot3>(Q, np, X, Y, Z, (float*)nullptr, cols, term, ctr);
     if (with_barrier) __syncthreads();
   }
   if (total == -1.2345) *sink = (float)total;

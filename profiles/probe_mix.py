@@ -16,7 +16,8 @@ stream = torch.cuda.current_stream().cuda_stream
 props = torch.cuda.get_device_properties(0)
 sms, clk = props.multi_processor_count, 1.965e9
 modes = {1: ("8 FFMA", 8), 2: ("8 MUFU.RSQ", 8), 3: ("8 FFMA2", 8), 4: ("6 FFMA2 + 2 MUFU.RSQ", 8),
-         5: ("6 FFMA + 2 MUFU.RSQ", 8), 6: ("12 FFMA + 2 MUFU.RSQ", 14)}
+         5: ("6 FFMA + 2 MUFU.RSQ", 8), 6: ("12 FFMA + 2 MUFU.RSQ", 14),
+         7: ("6 FFMA2 + 2 MUFU + LDS.128", 9)}
 for threads, per_sm in ((256, 8), (128, 8), (64, 8)):
     for mode, (name, n_instr) in modes.items():
         blocks, iters = sms * per_sm, 1 << 14
@@ -30,5 +31,5 @@ for threads, per_sm in ((256, 8), (128, 8), (64, 8)):
             best = min(best, e0.elapsed_time(e1) * 1e-3)
         warp_instr = n_instr * iters * blocks * threads / 32
         cycles_per_round = best * clk * sms * 4 / (iters * blocks * threads / 32)
-        print(f"{threads:4d} thr x {per_sm}/SM  {name:24s} {warp_instr / best / clk / sms / 4:.3f} warp-instr/clk/SMSP"
+        print(f"{threads:4d} thr x {per_sm}/SM  {name:26s} {warp_instr / best / clk / sms / 4:.3f} warp-instr/clk/SMSP"
               f"  ({cycles_per_round:.2f} SMSP-cycles per round of {n_instr})")
