@@ -67,7 +67,28 @@ int mu_kind(double mu, int* mu_int) {
 // idles while the chain's control section runs, and with one or two warps per chain that
 // loss (almost) disappears while 8-10 resident chains still keep the pipes busy.  Large
 // molecules (one or two chains per SM) get 16 / 8 warps per chain instead.
-int auto_threads(int n_atoms, int smem_bytes, int compute_dtype) {
+int sm_count() {  // SMs of the current device (queried once per device)
+  static int cache[64] = {0};
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 148;
+  if (cache[dev] == 0) {
+    int n = 0;
+    cache[dev] = (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && n > 0) ? n : 148;
+  }
+  return cache[dev];
+}
+
+// Block size when the caller leaves it open.  Batches that fill the GPU: few warps per chain
+// and as many resident chains as shared memory allows (measured best).
+// At most one chain per SM (the single-molecule drop-in calls): nothing else hides the
+// chain's latency, so it gets up to 16 warps (profiles/single_chain_kernel.py: a 1000-atom
+// chain 16.7 -> 9.7 us per step in fp64, 8.1 -> 5.3 in fp32).
+int auto_threads(int n_atoms, int n_chains, int smem_bytes, int compute_dtype) {
+  if (n_chains <= sm_count()) {
+    if (n_atoms <= 128) return compute_dtype == MCH_F64 ? 128 : 32;
+    const int t = ((n_atoms / 2 + 31) / 32) * 32;
+    return t < 128 ? 128 : (t > 512 ? 512 : t);
+  }
   if (n_atoms <= 128) return 32;
   const int chains_per_sm = kMaxSmem / smem_bytes;
   if (chains_per_sm >= 3) return compute_dtype == MCH_F64 ? 128 : 64;
@@ -253,7 +274,7 @@ int mch_optimize_batch(const mch_optimize_desc* d, void* stream) {
   const int smem = mch_optimize_smem_bytes(d->n_atoms, d->n_subunits, d->n_bonds, d->max_subunit_atoms, d->compute_dtype);
   if (smem < 0) return smem;
   int threads;
-  int rc = check_threads(d->threads_per_chain, auto_threads(d->n_atoms, smem, d->compute_dtype),
+  int rc = check_threads(d->threads_per_chain, auto_threads(d->n_atoms, d->n_chains, smem, d->compute_dtype),
                          d->compute_dtype == MCH_F64 ? 512 : 1024, &threads);
   if (rc != MCH_OK) return rc;
 
@@ -316,7 +337,10 @@ int mch_collapse_batch(const mch_collapse_desc* d, void* stream) {
     return fail(MCH_ERR_INVALID, "mch_collapse_batch: trace buffers need trace_capacity > 0");
   if (d->n_atoms > (1 << 20) || d->n_subunits > (1 << 16)) return fail(MCH_ERR_TOO_LARGE, "molecule too large");
   int threads;
-  int rc = check_threads(d->threads_per_mol, d->n_atoms <= 128 ? 32 : (d->n_atoms <= 384 ? 64 : (d->n_atoms <= 3072 ? 128 : 256)), 256, &threads);
+  // few molecules (at most one per SM): latency case, a molecule gets the largest block that still has work
+  const int batch_threads = d->n_atoms <= 128 ? 32 : (d->n_atoms <= 384 ? 64 : (d->n_atoms <= 3072 ? 128 : 256));
+  const int alone_threads = d->n_atoms <= 128 ? 32 : (d->n_atoms <= 512 ? 128 : 256);
+  int rc = check_threads(d->threads_per_mol, d->n_mol <= sm_count() ? alone_threads : batch_threads, 256, &threads);
   if (rc != MCH_OK) return rc;
   const mch::ColLayout L = mch::col_layout(d->n_atoms, d->n_subunits, d->n_bonds, d->compute_dtype == MCH_F64 ? 8 : 4);
   if (L.total > kMaxSmem) return fail(MCH_ERR_TOO_LARGE, "molecule needs %d B of shared memory (limit %d)", L.total, kMaxSmem);
