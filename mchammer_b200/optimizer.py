@@ -194,14 +194,16 @@ class Optimizer:
         topo, out = self._run_single(mol, bond_pair_ids, subunits, want_trace=True)
         trace = out.trace_potentials[0].cpu().numpy()
         bond, passed, _, _ = unpack_info(out.trace_info[0].cpu().numpy())
-        frames = out.trajectory[0].cpu().numpy().astype(np.float64)
-        bond_table = np.asarray(bond_pair_ids)
-        for step in range(trace.shape[0]):
-            u, unb, far = (float(x) for x in trace[step])
+        frames = np.asarray(out.trajectory[0].cpu().numpy(), dtype=np.float64)
+        # the log prints the chosen bond as numpy prints a row of the bond table: format each row once
+        bond_rows = [str(row) for row in np.asarray(bond_pair_ids)]
+        trace = trace.tolist()
+        for step in range(len(trace)):
+            u, unb, far = trace[step]
             if passed[step] < 0:
                 flag, row = None, None
             else:
-                flag, row = bool(passed[step]), bond_table[int(bond[step])]
+                flag, row = bool(passed[step]), bond_rows[int(bond[step])]
             result.add_step_result(
                 MCStepResult(
                     step=step, position_matrix=frames[step], passed=flag, system_potential=u,
@@ -345,15 +347,16 @@ class Optimizer:
         rule = "=" * 52 + "\n"
         result.update_log(rule + " " * 17 + "Running optimisation!" + " " * 14 + "\n" + rule + "\n")
         result.update_log("step system_potential nonbond_potential max_dist opt_bbs updated?\n")
-        bond_table = np.asarray(bond_pair_ids)
+        bond_rows = [str(row) for row in np.asarray(bond_pair_ids)]
+        us, unbs = traj.system_potential[chain].tolist(), traj.nonbonded_potential[chain].tolist()
+        fars, flags = traj.max_bond_distance[chain].tolist(), traj.passed[chain].tolist()
+        picks = traj.bond_index[chain].tolist()
         for step in range(traj.num_steps):
-            u = float(traj.system_potential[chain, step])
-            unb = float(traj.nonbonded_potential[chain, step])
-            far = float(traj.max_bond_distance[chain, step])
-            if traj.passed[chain, step] < 0:
+            u, unb, far = us[step], unbs[step], fars[step]
+            if flags[step] < 0:
                 flag, row = None, None
             else:
-                flag, row = bool(traj.passed[chain, step]), bond_table[int(traj.bond_index[chain, step])]
+                flag, row = bool(flags[step]), bond_rows[picks[step]]
             frame = None if traj.positions is None else np.array(traj.positions[chain, step], dtype=np.float64)
             result.add_step_result(
                 MCStepResult(
