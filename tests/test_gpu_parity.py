@@ -258,6 +258,53 @@ def test_batch_with_per_chain_positions_and_ragged_subunits():
         assert np.allclose(got.positions[c], want.final_positions, rtol=RTOL64, atol=1e-9)
 
 
+@pytest.mark.parametrize("seed", range(12))
+def test_random_molecules_against_oracle(seed):
+    # seeded fuzz: random sizes, ragged random partitions (some atoms in no subunit), random
+    # bond lists (intra- and cross-subunit, repeated atoms), parameters and exponents -- fp64
+    # mode must give the oracle's accept/reject sequence, potentials and geometry
+    rng = np.random.default_rng(1234 + seed)
+    n = int(rng.integers(2, 260))
+    n_sub = int(rng.integers(1, min(n, 24) + 1))
+    labels = rng.integers(0, n_sub, size=n)
+    loose = rng.random(n) < (0.1 if seed % 3 == 0 else 0.0)
+    members = {k: [int(i) for i in np.flatnonzero((labels == k) & ~loose)] for k in range(n_sub)}
+    subunits = {int(100 - k): (v if k % 2 else v[::-1]) for k, v in members.items() if v}
+    owned = sorted(i for v in subunits.values() for i in v)
+    if len(owned) < 2:
+        pytest.skip("degenerate draw")
+    # well separated random points: jittered grid, so no pair is closer than ~0.6
+    side = int(np.ceil(n ** (1 / 3)))
+    grid = np.array([(x, y, z) for x in range(side) for y in range(side) for z in range(side)], dtype=float)
+    pos = 1.7 * grid[rng.permutation(len(grid))[:n]] + rng.uniform(-0.4, 0.4, size=(n, 3)) + rng.normal(scale=30.0, size=3)
+    n_bonds = int(rng.integers(1, 9))
+    bonds = []
+    while len(bonds) < n_bonds:
+        a, b = (int(x) for x in rng.choice(owned, size=2, replace=False))
+        bonds.append((a, b) if rng.random() < 0.5 else [b, a])
+    mu = float(rng.choice([3.0, 3.0, 2.0, 4.0, 2.5, 6.0]))
+    steps = int(rng.integers(2, 90))
+    kwargs = dict(step_size=float(rng.uniform(0.05, 0.5)), target_bond_length=float(rng.uniform(0.8, 3.0)),
+                  num_steps=steps, bond_epsilon=float(rng.uniform(1, 80)), nonbond_epsilon=float(rng.uniform(1, 40)),
+                  nonbond_sigma=float(rng.uniform(0.8, 1.6)), nonbond_mu=mu, beta=float(rng.uniform(0.2, 4.0)))
+    mol = mch.Molecule(atoms=[mch.Atom(i, "C") for i in range(n)], bonds=[], position_matrix=pos)
+    opt = mch.Optimizer(random_seed=77 + seed, **kwargs)
+    out_mol, result = opt.get_trajectory(mol, bonds, subunits)
+    want = orc.optimizer_run(pos, bonds, subunits, orc.OptimizerParams(**kwargs), np.random.default_rng(77 + seed))
+    props = list(result.get_steps_properties())
+    passed = np.array([-1 if p["passed"] is None else int(p["passed"]) for _, p in props])
+    assert np.array_equal(passed, want.passed), "accept/reject sequence differs from the oracle"
+    assert rel_close([p["system_potential"] for _, p in props], want.system_potential, RTOL64)
+    assert rel_close([p["nonbonded_potential"] for _, p in props], want.nonbonded_potential, RTOL64)
+    assert rel_close([p["max_bond_distance"] for _, p in props], want.max_bond_distance, RTOL64)
+    assert np.allclose(out_mol.get_position_matrix(), want.final_positions, rtol=RTOL64, atol=1e-9)
+    # the same chain through the batched entry point in fp32: potential within the stated tolerance
+    # as long as the two precisions took the same decisions
+    fast = mch.Optimizer(precision="fp32", **kwargs).get_results_batch(mol, bonds, subunits, seeds=[77 + seed])
+    if int(fast.n_accepted[0]) == int((want.passed == 1).sum()):
+        assert rel_close(fast.system_potential[0], want.system_potential[-1], RTOL32)
+
+
 def test_fp32_mode_tolerance_against_reference():
     # fp32 fast mode: potentials within 1e-4 relative (north_star).  Trajectories may fork
     # once an accept test lands within fp32 noise, so compare the common prefix of the
@@ -544,6 +591,39 @@ def test_collapser_full_size_cage_block_dealing(threads):
         assert int(out.steps_run[m].item()) == want.steps_run
         assert rel_close(out.min_distance[m].item(), want.min_distance, RTOL64)
         assert np.allclose(out.positions[m].cpu().numpy(), want.final_positions, rtol=RTOL64, atol=1e-9)
+
+
+@pytest.mark.parametrize("seed", range(8))
+def test_collapser_random_clusters_against_oracle(seed):
+    # seeded fuzz: 2-9 clusters of 1-70 atoms with random hydrogens (a cluster may be all H but one),
+    # subunit ids interleaved with atom order, random step / threshold / scaling
+    rng = np.random.default_rng(4321 + seed)
+    n_sub = int(rng.integers(2, 10))
+    sizes = [int(rng.integers(1, 71)) for _ in range(n_sub)]
+    centres = rng.normal(scale=14.0, size=(n_sub, 3))
+    pos = np.concatenate([c + rng.normal(scale=1.5, size=(k, 3)) for c, k in zip(centres, sizes)])
+    n = pos.shape[0]
+    owner = np.repeat(np.arange(n_sub), sizes)
+    order = rng.permutation(n)           # atom ids are shuffled with respect to the clusters
+    pos, owner = pos[order], owner[order]
+    elements = ["H" if rng.random() < 0.35 else "C" for _ in range(n)]
+    for k in range(n_sub):               # every subunit keeps at least one heavy atom
+        ids = np.flatnonzero(owner == k)
+        if all(elements[i] == "H" for i in ids):
+            elements[int(ids[0])] = "N"
+    subunits = {int(7 * k + 1): [int(i) for i in np.flatnonzero(owner == k)] for k in rng.permutation(n_sub)}
+    bonds = tuple((int(a), int(b)) for a, b in (rng.choice(n, size=2, replace=False) for _ in range(int(rng.integers(1, 6)))))
+    step, thr, scale = float(rng.uniform(0.02, 0.12)), float(rng.uniform(1.0, 2.2)), bool(rng.random() < 0.5)
+    mol = mch.Molecule(atoms=[mch.Atom(i, e) for i, e in enumerate(elements)], bonds=[], position_matrix=pos)
+    is_h = [e == "H" for e in elements]
+    want = orc.collapser_run(pos, is_h, bonds, subunits, step, thr, scale)
+    coll = mch.Collapser(step_size=step, distance_threshold=thr, scale_steps=scale)
+    got = coll.get_results_batch(mol, bonds, subunits, pos[None])
+    assert int(got.steps_run[0]) == want.steps_run
+    assert rel_close(got.min_distance[0], want.min_distance, RTOL64)
+    assert np.allclose(got.positions[0], want.final_positions, rtol=RTOL64, atol=1e-9)
+    if want.steps_run:
+        assert rel_close(got.max_bond_distance[0], want.max_bond_distance[-1], RTOL64)
 
 
 def test_collapser_never_touching_raises():
