@@ -143,7 +143,7 @@ class BatchPlan:
         self.threads_per_chain = int(threads_per_chain)
         self.per_chain_positions = bool(per_chain_positions)
         # `run` cuts every device's chains into slices and pipelines H2D / kernel / D2H of
-        # consecutive slices on side streams (0 = choose: 4 slices once the batch is large)
+        # consecutive slices on side streams (0 = choose: 4 slices once the copies are worth hiding)
         self.n_slices = int(n_slices)
         self.io_dtype = np.dtype(io_dtype)
         if self.io_dtype not in (np.dtype(np.float64), np.dtype(np.float32)):
@@ -242,7 +242,9 @@ class BatchPlan:
         )
 
     def _slices(self, count: int) -> list[tuple[int, int]]:
-        n = self.n_slices if self.n_slices > 0 else (4 if count >= 2048 else 1)
+        # automatic: pipeline in 4 slices once a device's share of the copies is worth hiding (>= 16 MiB)
+        per_chain = self.topo.n_atoms * 3 * self.h_pos_out.element_size()
+        n = self.n_slices if self.n_slices > 0 else (4 if count >= 8 and count * per_chain >= (16 << 20) else 1)
         n = max(1, min(n, count))
         return [b for b in shard_bounds(count, n) if b[1] > b[0]]
 
