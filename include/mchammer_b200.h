@@ -64,6 +64,8 @@ typedef struct mch_optimize_desc {
   int32_t compute_dtype;      /* MCH_F64: parity mode; MCH_F32: fast mode                */
   int32_t inexact_undo;       /* 1: on reject redo (p - v) + v like optimizer.py:273-277 */
   int32_t threads_per_chain;  /* 0 = auto; else multiple of 32, <= 1024 (fp32) / 512 (fp64) */
+  int32_t cluster_size;       /* CTAs (SMs) per chain: 0 = auto, 1 = one CTA, 2 / 4 / 8 = thread-block cluster */
+  int32_t reserved;           /* 0                                                      */
   const void* pos_in;         /* [dev] [n_chains or 1][n_atoms][3]                        */
   int64_t pos_in_chain_stride;/* elements between chains; 0 = all chains start from chain 0 */
   void* pos_out;              /* [dev] [n_chains][n_atoms][3]                             */

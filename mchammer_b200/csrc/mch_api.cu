@@ -239,8 +239,13 @@ namespace {
 // is negligible next to the sweep, and the buffer is dropped when it would cost a resident
 // chain (the 5004-atom cage: 115 KB with it -> one chain per SM, 95 KB without -> two) or
 // would not fit at all.
-int plan_chain_smem(int n_atoms, int n_subunits, int n_bonds, int max_su, int compute_dtype, int* defer) {
+int plan_chain_smem(int n_atoms, int n_subunits, int n_bonds, int max_su, int compute_dtype, int* defer,
+                    int cluster = 1) {
   const int tsize = compute_dtype == MCH_F64 ? 8 : 4;
+  if (cluster > 1) {  // a chain on a cluster always defers (the partial energy rows travel under the sweep)
+    *defer = 1;
+    return mch::opt_layout(n_atoms, n_subunits, n_bonds, max_su, tsize, 1, cluster).total;
+  }
   const int with = mch::opt_layout(n_atoms, n_subunits, n_bonds, max_su, tsize, 1).total;
   const int without = mch::opt_layout(n_atoms, n_subunits, n_bonds, max_su, tsize, 0).total;
   const bool keep = with <= kMaxSmem && (kMaxSmem / with >= 3 || kMaxSmem / with == kMaxSmem / without);
@@ -271,12 +276,40 @@ int mch_optimize_batch(const mch_optimize_desc* d, void* stream) {
   if (!d->pos_in || !d->pos_out || !d->perm || !d->su_offsets || !d->bonds || !d->bond_su || !d->rng_state ||
       !d->system_potential || !d->nonbonded_potential || !d->max_bond_distance || !d->n_accepted || !d->last_step_info)
     return fail(MCH_ERR_INVALID, "mch_optimize_batch: null required pointer");
-  const int smem = mch_optimize_smem_bytes(d->n_atoms, d->n_subunits, d->n_bonds, d->max_subunit_atoms, d->compute_dtype);
+  int smem = mch_optimize_smem_bytes(d->n_atoms, d->n_subunits, d->n_bonds, d->max_subunit_atoms, d->compute_dtype);
   if (smem < 0) return smem;
+  // Thread-block cluster per chain: worth it when the GPU would otherwise be mostly idle and the
+  // sweep is long enough to pay for one cluster barrier per step (big molecule, few chains).
+  int cluster = d->cluster_size;
+  if (cluster != 0 && cluster != 1 && cluster != 2 && cluster != 4 && cluster != 8)
+    return fail(MCH_ERR_INVALID, "mch_optimize_batch: cluster_size must be 0 (auto), 1, 2, 4 or 8, got %d", cluster);
+  if (cluster == 0) {
+    cluster = 1;
+    if (d->n_atoms >= 2048 && d->num_steps > 1) {
+      const int sms = sm_count();
+      for (int g = 8; g >= 2; g /= 2)
+        if ((long long)d->n_chains * g <= sms) {
+          int defer_unused;
+          if (plan_chain_smem(d->n_atoms, d->n_subunits, d->n_bonds, d->max_subunit_atoms, d->compute_dtype,
+                              &defer_unused, g) <= kMaxSmem) cluster = g;
+          break;
+        }
+    }
+  }
+  int defer = 0;
+  if (cluster > 1) {
+    smem = plan_chain_smem(d->n_atoms, d->n_subunits, d->n_bonds, d->max_subunit_atoms, d->compute_dtype, &defer, cluster);
+    if (smem > kMaxSmem)
+      return fail(MCH_ERR_TOO_LARGE, "a chain on a cluster needs %d B of shared memory per CTA (limit %d)", smem, kMaxSmem);
+  } else {
+    (void)plan_chain_smem(d->n_atoms, d->n_subunits, d->n_bonds, d->max_subunit_atoms, d->compute_dtype, &defer);
+  }
   int threads;
-  int rc = check_threads(d->threads_per_chain, auto_threads(d->n_atoms, d->n_chains, smem, d->compute_dtype),
+  int rc = check_threads(d->threads_per_chain,
+                         cluster > 1 ? 512 : auto_threads(d->n_atoms, d->n_chains, smem, d->compute_dtype),
                          d->compute_dtype == MCH_F64 ? 512 : 1024, &threads);
   if (rc != MCH_OK) return rc;
+  if (cluster > 1 && threads < 64) return fail(MCH_ERR_INVALID, "a chain on a cluster needs at least 64 threads per CTA");
 
   mch::OptArgs a;
   a.pos_in = d->pos_in; a.pos_in_stride = d->pos_in_chain_stride; a.pos_out = d->pos_out;
@@ -291,7 +324,8 @@ int mch_optimize_batch(const mch_optimize_desc* d, void* stream) {
   a.trace_f = d->trace_potentials; a.trace_i = d->trace_info; a.traj = d->trajectory;
   a.pairs = reinterpret_cast<unsigned long long*>(d->pair_evals);
   a.inexact_undo = d->inexact_undo;
-  (void)plan_chain_smem(d->n_atoms, d->n_subunits, d->n_bonds, d->max_subunit_atoms, d->compute_dtype, &a.defer);
+  a.defer = defer;
+  a.cluster = cluster;
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
   const bool io_f64 = d->io_dtype == MCH_F64;
   return d->compute_dtype == MCH_F64 ? mch::launch_optimize_f64(io_f64, mk, a, threads, smem, s)

@@ -20,6 +20,29 @@ int launch(K kernel, const A& args, int blocks, int threads, int smem, cudaStrea
   return 0;
 }
 
+// Same, as thread-block clusters of `cluster` CTAs (blocks = chains x cluster).
+template <typename K, typename A>
+int launch_clustered(K kernel, const A& args, int blocks, int threads, int smem, int cluster, cudaStream_t stream,
+                     const char* what) {
+  cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  if (e != cudaSuccess) return fail(-3, "%s: cudaFuncSetAttribute(%d B): %s", what, smem, cudaGetErrorString(e));
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)blocks, 1, 1);
+  cfg.blockDim = dim3((unsigned)threads, 1, 1);
+  cfg.dynamicSmemBytes = (size_t)smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = (unsigned)cluster;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  e = cudaLaunchKernelEx(&cfg, kernel, args);
+  if (e != cudaSuccess) return fail(-3, "%s: cluster launch (%d CTAs per chain) failed: %s", what, cluster, cudaGetErrorString(e));
+  return 0;
+}
+
 // Kernel-variant dispatch of the resident Metropolis kernel (one TU per compute type, so the
 // instantiations compile in parallel).  io_f64: element type of the position arrays.
 int launch_optimize_f32(bool io_f64, int mu_kind, const OptArgs& a, int threads, int smem, cudaStream_t s);
@@ -36,8 +59,21 @@ int launch_optimize_nt(int mk, const OptArgs& a, int threads, int smem, cudaStre
   }
 }
 
+// a chain spread over a.cluster CTAs: the large-block instantiation, cluster-capable
+template <typename T, typename Tio>
+int launch_optimize_cluster(int mk, const OptArgs& a, int threads, int smem, cudaStream_t s) {
+  constexpr int NT = large_block<T>();
+  const int blocks = a.C * a.cluster;
+  switch (mk) {
+    case MU_3: return launch_clustered(mch_optimize_kernel<T, Tio, MU_3, NT, true>, a, blocks, threads, smem, a.cluster, s, "mch_optimize_batch");
+    case MU_INT: return launch_clustered(mch_optimize_kernel<T, Tio, MU_INT, NT, true>, a, blocks, threads, smem, a.cluster, s, "mch_optimize_batch");
+    default: return launch_clustered(mch_optimize_kernel<T, Tio, MU_REAL, NT, true>, a, blocks, threads, smem, a.cluster, s, "mch_optimize_batch");
+  }
+}
+
 template <typename T, typename Tio>
 int launch_optimize_io(int mk, const OptArgs& a, int threads, int smem, cudaStream_t s) {
+  if (a.cluster > 1) return launch_optimize_cluster<T, Tio>(mk, a, threads, smem, s);
   if (sizeof(T) == 4 && threads <= 32) return launch_optimize_nt<T, Tio, 32>(mk, a, threads, smem, s);
   if (sizeof(T) == 4 && threads <= 64) return launch_optimize_nt<T, Tio, 64>(mk, a, threads, smem, s);
   return threads <= small_block<T>() ? launch_optimize_nt<T, Tio, small_block<T>()>(mk, a, threads, smem, s)

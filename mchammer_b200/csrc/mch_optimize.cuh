@@ -37,6 +37,10 @@
 
 #include "mch_device.cuh"
 
+#ifdef __CUDACC__
+#include <cooperative_groups.h>
+#endif
+
 namespace mch {
 
 struct OptArgs {
@@ -64,6 +68,7 @@ struct OptArgs {
   unsigned long long* pairs; // [C] or null: pair terms evaluated
   int inexact_undo;          // 1: reproduce (p - v) + v on reject (fp64 parity)
   int defer;                 // 1: deferred control work + second column-sum buffer (see header)
+  int cluster;               // CTAs per chain (thread-block cluster; 1 = the chain is one CTA)
 };
 
 struct Ctl {
@@ -85,12 +90,14 @@ struct Ctl {
 
 // Shared-memory carve-up, identical on host (size query) and device.
 struct OptLayout {
-  int x, y, z, colsum, colsum_stride, rows, E, erow, csum, invn, wsum, suoff, bslot, bsu, ctl, total;
+  int x, y, z, colsum, colsum_stride, rows, E, erow, csum, invn, wsum, xsum, epart, suoff, bslot, bsu, ctl, total;
 };
 
 MCH_HD int align_up(int v, int a) { return (v + a - 1) / a * a; }
 
-MCH_HD OptLayout opt_layout(int N, int S, int B, int max_su, int tsize, int defer) {
+constexpr int kMaxCluster = 8;
+
+MCH_HD OptLayout opt_layout(int N, int S, int B, int max_su, int tsize, int defer, int cluster = 1) {
   OptLayout L;
   const int np = align_up(N, 8);
   int o = 0;
@@ -107,6 +114,9 @@ MCH_HD OptLayout opt_layout(int N, int S, int B, int max_su, int tsize, int defe
   L.csum = o; o += (S + 1) * 3 * 8;  // per-subunit coordinate sums + the molecule's
   L.invn = o; o += S * 8;
   L.wsum = o; o += 3 * 32 * 8;
+  // cluster mode: per-CTA sweep totals and per-CTA partial rows of E, each double buffered by step parity
+  L.xsum = o; o += cluster > 1 ? 2 * kMaxCluster * 8 : 0;
+  L.epart = o; o += cluster > 1 ? 2 * kMaxCluster * S * 8 : 0;
   L.suoff = o; o += align_up(S + 1, 4) * 4;
   L.bslot = o; o += align_up(2 * B, 4) * 4;
   L.bsu = o; o += align_up(2 * B, 4) * 4;
@@ -148,16 +158,23 @@ template <typename T, int NTMAX> constexpr int min_blocks_per_sm() {
          : NTMAX == small_block<T>() ? (sizeof(T) == 4 ? MCH_F32_THREADS_PER_SM : 512) / NTMAX : 1;
 }
 
-template <typename T, typename Tio, int MUK, int NTMAX>
+// CL: the instantiation can run a chain on a thread-block cluster of a.cluster CTAs (launched with
+// that cluster dimension).  Every CTA keeps the whole chain and runs the control section redundantly
+// -- same inputs, same arithmetic, same decisions -- and only the sweep's columns are split; what the
+// CTAs exchange through distributed shared memory, one cluster barrier per step, is the per-CTA sweep
+// total and, after an accept, the per-CTA partial sums of the new energy-table row.
+template <typename T, typename Tio, int MUK, int NTMAX, bool CL = false>
 __global__ void __launch_bounds__(NTMAX, (min_blocks_per_sm<T, NTMAX>()))
 mch_optimize_kernel(const __grid_constant__ OptArgs a) {
   extern __shared__ __align__(32) unsigned char smem[];
-  const int c = blockIdx.x;
+  const int G = CL ? a.cluster : 1;                  // CTAs of this chain
+  const int c = CL ? (int)blockIdx.x / G : (int)blockIdx.x;
+  const int rank = CL ? (int)blockIdx.x % G : 0;     // == %cluster_ctarank for a (G,1,1) cluster
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int nt = blockDim.x, nwarps = nt >> 5;
   const int N = a.N, S = a.S, B = a.B;
 
-  const OptLayout L = opt_layout(N, S, B, a.max_su, (int)sizeof(T), a.defer);
+  const OptLayout L = opt_layout(N, S, B, a.max_su, (int)sizeof(T), a.defer, G);
   T* X = reinterpret_cast<T*>(smem + L.x);
   T* Y = reinterpret_cast<T*>(smem + L.y);
   T* Z = reinterpret_cast<T*>(smem + L.z);
@@ -170,6 +187,8 @@ mch_optimize_kernel(const __grid_constant__ OptArgs a) {
   double* ctot = csum + 3 * S;  // coordinate sums of the whole molecule
   double* invn = reinterpret_cast<double*>(smem + L.invn);
   double* wsum = reinterpret_cast<double*>(smem + L.wsum);   // 3 x 32: [0..31] cross, [32..63] intra
+  double* xsum = reinterpret_cast<double*>(smem + L.xsum);   // cluster: [parity][rank] sweep totals
+  double* epart = reinterpret_cast<double*>(smem + L.epart); // cluster: [parity][rank][S] partial rows of E
   int* suoff = reinterpret_cast<int*>(smem + L.suoff);
   int* bslot = reinterpret_cast<int*>(smem + L.bslot);
   int* bsu = reinterpret_cast<int*>(smem + L.bsu);
@@ -219,6 +238,7 @@ mch_optimize_kernel(const __grid_constant__ OptArgs a) {
   for (int k = tid; k < S * S; k += nt) E[k] = 0.0;
   for (int k = tid; k < S; k += nt) invn[k] = 1.0 / (double)(suoff[k + 1] - suoff[k]);
   __syncthreads();
+  if (CL && G > 1) cooperative_groups::this_cluster().sync();  // every CTA's E is zeroed before any peer writes rows into it
 
   // ---------------------------------------------------------------- control-warp state
   // (uniform across the 32 lanes of warp 0; other warps never read it)
@@ -305,7 +325,7 @@ mch_optimize_kernel(const __grid_constant__ OptArgs a) {
     return warp_sum(e);
   };
   auto write_trace = [&](int step, double longest) {
-    if (lane == 0) {
+    if (lane == 0 && rank == 0) {
       if (a.trace_f) {
         double* t = a.trace_f + ((long long)c * a.num_steps + step) * 3;
         t[0] = U; t[1] = Unb; t[2] = longest;
@@ -351,6 +371,34 @@ mch_optimize_kernel(const __grid_constant__ OptArgs a) {
       erow[s] = v;
     }
     __syncwarp();
+  };
+  // Cluster mode.  This CTA's share of the new row `row` of E after an accepted move: sums over the
+  // columns it swept (column range [o_lo, o_hi) of the sweep that excluded `row`), pushed into slot
+  // [parity][rank] of EVERY CTA's epart through distributed shared memory.
+  auto push_partial_row = [&](const T* cs, int row, int parity) {
+    namespace cg = cooperative_groups;
+    cg::cluster_group cluster = cg::this_cluster();
+    const int g0 = suoff[row], g1 = suoff[row + 1];
+    int o_lo, o_hi;
+    sweep_part_columns(N - (g1 - g0), rank, G, o_lo, o_hi);
+    for (int t = 0; t < S; ++t) {
+      double v = 0.0;
+      if (t != row) {
+        const int shift = t > row ? (g1 - g0) : 0;  // slot = column + shift (columns skip the gap)
+        const int j_lo = max(suoff[t], o_lo + shift), j_hi = min(suoff[t + 1], o_hi + shift);
+        for (int j = j_lo + lane; j < j_hi; j += 32) v += (double)cs[j];
+        v = warp_sum(v) * scale;
+      }
+      if (lane < G) cluster.map_shared_rank(epart, lane)[(parity * kMaxCluster + rank) * S + t] = v;
+    }
+  };
+  auto install_partial_rows = [&](int row, int parity) {  // E[row][t] = sum over CTAs, rank order
+    for (int t = lane; t < S; t += 32) {
+      if (t == row) continue;
+      double v = 0.0;
+      for (int r = 0; r < G; ++r) v += epart[(parity * kMaxCluster + r) * S + t];
+      E[row * S + t] = v; E[t * S + row] = v;
+    }
   };
   // CRITICAL-PATH half of a proposal: the draws of optimizer.py:214-244, the translation
   // vector, the displaced rows Q and the sweep descriptor.  The other warps are waiting at
@@ -410,7 +458,12 @@ mch_optimize_kernel(const __grid_constant__ OptArgs a) {
     if (lane == 0) ctl->U = 0.0;  // accumulates the intra-subunit sum during step 0
     __syncwarp();
   }
+  // On a cluster the subunits are dealt to the CTAs (boustrophedon, so that the shrinking column
+  // ranges balance): a CTA computes complete rows E[s][t > s] and the intra-subunit sums of ITS
+  // subunits, then pushes them to every peer -- one cluster barrier for the whole of step 0.
+  auto step0_owner = [&](int s) { const int q = s / G, m = s - q * G; return (q & 1) ? G - 1 - m : m; };
   for (int s = 0; s < S; ++s) {
+    if (CL && G > 1 && step0_owner(s) != rank) continue;
     if (warp == 0) {
       const int n = fill_rows(s, (T)0, (T)0, (T)0);
       if (lane == 0) { ctl->nrows = n; ctl->c0 = suoff[s + 1]; ctl->g0 = suoff[s + 1]; ctl->g1 = suoff[s + 1]; ctl->c1 = N; ctl->ms = s; ctl->buf = 0; }
@@ -434,6 +487,23 @@ mch_optimize_kernel(const __grid_constant__ OptArgs a) {
       regroup(colsum, s, s + 1);
     }
   }
+  if (CL && G > 1) {
+    namespace cg = cooperative_groups;
+    cg::cluster_group cluster = cg::this_cluster();
+    __syncthreads();  // this CTA's rows and its intra-subunit sum are complete
+    for (int r = 0; r < G; ++r) {
+      if (r == rank) continue;
+      double* peer = cluster.map_shared_rank(E, r);
+      for (int own = 0; own < S; ++own) {
+        if (step0_owner(own) != rank) continue;
+        for (int t = own + 1 + tid; t < S; t += nt) { const double v = E[own * S + t]; peer[own * S + t] = v; peer[t * S + own] = v; }
+      }
+    }
+    if (tid < G) cluster.map_shared_rank(xsum, tid)[rank] = ctl->U;  // parity-0 slots (the step loop starts with parity 1)
+    cluster.sync();
+    if (tid == 0) { double u = 0.0; for (int r = 0; r < G; ++r) u += xsum[r]; ctl->U = u; }
+    __syncthreads();
+  }
   if (warp == 0) {
     __syncwarp();
     rng = pcg_load(a.rng + 6LL * c);
@@ -447,7 +517,7 @@ mch_optimize_kernel(const __grid_constant__ OptArgs a) {
     U = Unb + bond_terms(-1, (T)0, (T)0, (T)0, longest);
     info = -1;
     write_trace(0, longest);
-    if (a.num_steps <= 1 && lane == 0) a.maxd[c] = longest;
+    if (a.num_steps <= 1 && lane == 0 && rank == 0) a.maxd[c] = longest;
     __syncwarp();
     if (a.num_steps > 1) {
       propose(1);
@@ -458,7 +528,7 @@ mch_optimize_kernel(const __grid_constant__ OptArgs a) {
   // ---------------------------------------------------------------- Monte-Carlo steps
   for (int step = 1; step < a.num_steps; ++step) {
     __syncthreads();  // A: move published, positions of step-1 final
-    if (a.traj) {
+    if (a.traj && rank == 0) {
       const long long frame = ((long long)c * a.num_steps + (step - 1)) * N * 3;
       for (int n = tid; n < N; n += nt) {
         const long long dst = frame + 3LL * a.perm[n];
@@ -474,9 +544,14 @@ mch_optimize_kernel(const __grid_constant__ OptArgs a) {
       // (2) trace record of the previous step, (3) bond energy of the trial geometry.
       if (kDefer) {
         if (d_accepted) {
-          regroup(colsum + d_buf * colsum_stride, d_ms, 0);
-          refresh_erow();
-          d_accepted = false;
+          if (CL && G > 1) {
+            // this CTA's share of the new row goes to every CTA; installed after this step's cluster barrier
+            push_partial_row(colsum + d_buf * colsum_stride, d_ms, step & 1);
+          } else {
+            regroup(colsum + d_buf * colsum_stride, d_ms, 0);
+            refresh_erow();
+            d_accepted = false;
+          }
         }
         if (d_step > 0 && (a.trace_f || a.trace_i)) {
           double longest = 0.0;
@@ -494,15 +569,36 @@ mch_optimize_kernel(const __grid_constant__ OptArgs a) {
       // warp 0 spends roughly the time of 100 rows x 32 columns on the deferred control work:
       // one pair of column units less for subunits of up to ~50 atoms, nothing for large ones
       const int handicap = kDefer ? min(1, 50 / ctl->nrows) : 0;
-      double part = pair_sweep<T, MUK, false, true, kXF, kX2, kRot3>(Q, ctl->nrows, X, Y, Z, colsum + ctl->buf * colsum_stride, others, term, ctr, handicap);
+      double part = pair_sweep<T, MUK, false, true, kXF, kX2, kRot3>(Q, ctl->nrows, X, Y, Z, colsum + ctl->buf * colsum_stride, others, term, ctr, handicap, rank, G);
       part = warp_sum(part);
       if (lane == 0) wsum[warp] = part;
     }
     __syncthreads();  // B: column sums and warp totals published
+    if (CL && G > 1) {
+      // every CTA of the chain learns every CTA's sweep total (slots double buffered by step parity:
+      // a CTA that runs ahead cannot overwrite a slot a slower one still has to read)
+      namespace cg = cooperative_groups;
+      cg::cluster_group cluster = cg::this_cluster();
+      if (warp == 0) {
+        double mine = 0.0;
+        for (int w = 0; w < nwarps; ++w) mine += wsum[w];
+        if (lane < G) cluster.map_shared_rank(xsum, lane)[(step & 1) * kMaxCluster + rank] = mine;
+      }
+      cluster.sync();
+    }
     if (warp == 0) {
       unpark();
       double fresh = 0.0;
-      for (int w = 0; w < nwarps; ++w) fresh += wsum[w];
+      if (CL && G > 1) {
+        for (int r = 0; r < G; ++r) fresh += xsum[(step & 1) * kMaxCluster + r];
+        if (d_accepted) {  // the row pushed under this step's sweep: needed from here on (erow below)
+          install_partial_rows(d_ms, step & 1);
+          refresh_erow();
+          d_accepted = false;
+        }
+      } else {
+        for (int w = 0; w < nwarps; ++w) fresh += wsum[w];
+      }
       fresh *= scale;
       const double Unb_new = Unb + (fresh - erow[ms]);
       const double U_new = Unb_new + Ub_trial;
@@ -559,9 +655,13 @@ mch_optimize_kernel(const __grid_constant__ OptArgs a) {
     double longest;
     (void)bond_terms(-1, (T)0, (T)0, (T)0, longest);
     write_trace(a.num_steps - 1, longest);
-    if (lane == 0) a.maxd[c] = longest;
+    if (lane == 0 && rank == 0) a.maxd[c] = longest;
   }
   __syncthreads();
+  if (CL && G > 1) {
+    cooperative_groups::this_cluster().sync();  // no CTA leaves while another may still write into it
+    if (rank != 0) return;                      // CTA 0 reports the chain
+  }
 
   // ---------------------------------------------------------------- epilogue
   for (int n = tid; n < N; n += nt) {

@@ -99,6 +99,7 @@ def optimize_on_device(
     want_trajectory: bool = False,
     threads_per_chain: int = 0,
     out: OptimizeOutput | None = None,
+    cluster_size: int = 0,
 ) -> OptimizeOutput:
     """Launch the resident Metropolis kernel for ``n_chains`` chains (asynchronous)."""
     torch = native.require_cuda()
@@ -150,6 +151,7 @@ def optimize_on_device(
         desc.io_dtype, desc.compute_dtype = io_code, compute_code
         desc.inexact_undo = 1 if inexact_undo else 0
         desc.threads_per_chain = int(threads_per_chain)
+        desc.cluster_size, desc.reserved = int(cluster_size), 0
         desc.pos_in = ptr(pos_in)
         desc.pos_in_chain_stride = 0 if pos_in.shape[0] == 1 and n_chains > 1 else n * 3
         desc.pos_out = ptr(out.positions)

@@ -43,7 +43,7 @@ class OptimizeDesc(C.Structure):
         ("n_chains", C.c_int32), ("n_atoms", C.c_int32), ("n_subunits", C.c_int32),
         ("n_bonds", C.c_int32), ("max_subunit_atoms", C.c_int32), ("num_steps", C.c_int32),
         ("io_dtype", C.c_int32), ("compute_dtype", C.c_int32), ("inexact_undo", C.c_int32),
-        ("threads_per_chain", C.c_int32),
+        ("threads_per_chain", C.c_int32), ("cluster_size", C.c_int32), ("reserved", C.c_int32),
         ("pos_in", C.c_void_p), ("pos_in_chain_stride", C.c_int64), ("pos_out", C.c_void_p),
         ("perm", C.c_void_p), ("su_offsets", C.c_void_p), ("bonds", C.c_void_p),
         ("bond_su", C.c_void_p),

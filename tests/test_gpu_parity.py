@@ -459,6 +459,45 @@ def test_large_cage_against_oracle_both_precisions():
     assert np.allclose(fast.positions[0], want.final_positions, rtol=0, atol=1e-3)
 
 
+@pytest.mark.parametrize("cluster", [2, 4, 8])
+@pytest.mark.parametrize("precision", ["fp64", "fp32"])
+def test_chain_on_a_thread_block_cluster(cluster, precision):
+    # one chain spread over 2 / 4 / 8 CTAs (every CTA runs the control section redundantly, the sweep's
+    # columns are split, totals and new energy-table rows travel through distributed shared memory):
+    # same decisions and, up to the grouping of the sums, the same numbers as the one-CTA chain;
+    # fp64 also against the oracle
+    from mchammer_b200 import engine, rngstate
+    from mchammer_b200.lowering import lower_topology
+    import torch
+
+    mol, long_bonds, subunits = synthetic.cube_cage()
+    steps, seeds = 90, [11, 12, 13]
+    opt = mch.Optimizer(step_size=0.25, target_bond_length=1.2, num_steps=steps, precision=precision)
+    topo = lower_topology(mol.get_num_atoms(), long_bonds, subunits)
+    dtopo = engine.upload_topology(topo, 0)
+    pos = torch.from_numpy(mol.get_position_matrix()).cuda()
+
+    def run(g):
+        rng = engine.rng_words_to_device(rngstate.seed_states(seeds), torch.device("cuda", 0))
+        out = engine.optimize_on_device(dtopo, pos, len(seeds), rng, opt._params(), steps, precision,
+                                        want_trace=True, cluster_size=g)
+        return (out.system_potential.cpu().numpy(), out.n_accepted.cpu().numpy(), out.positions.cpu().numpy(),
+                out.trace_info.cpu().numpy(), out.rng_state.cpu().numpy())
+
+    u1, acc1, p1, info1, rng1 = run(1)
+    ug, accg, pg, infog, rngg = run(cluster)
+    assert np.array_equal(info1, infog), "a chain on a cluster took different decisions"
+    assert np.array_equal(acc1, accg) and np.array_equal(rng1, rngg)
+    assert rel_close(ug, u1, 1e-12 if precision == "fp64" else 1e-5)
+    assert np.allclose(pg, p1, rtol=0, atol=1e-9 if precision == "fp64" else 1e-4)
+    if precision == "fp64":
+        p = orc.OptimizerParams(step_size=0.25, target_bond_length=1.2, num_steps=steps)
+        want = orc.optimizer_run(mol.get_position_matrix(), long_bonds, subunits, p, np.random.default_rng(seeds[0]))
+        assert int(accg[0]) == int((want.passed == 1).sum())
+        assert rel_close(ug[0], want.system_potential[-1], RTOL64)
+        assert np.allclose(pg[0], want.final_positions, rtol=RTOL64, atol=1e-9)
+
+
 @pytest.mark.parametrize("precision", ["fp64", "fp32"])
 def test_threads_per_chain_does_not_change_the_chain(precision):
     # block size only changes how the pair sum is partitioned (rounding at the 1e-16 / 1e-7 level)

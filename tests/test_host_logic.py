@@ -194,7 +194,7 @@ def test_library_exports_every_declared_symbol():
 def test_ctypes_structs_match_header_layout():
     # sizes follow from the field lists in include/mchammer_b200.h (natural alignment)
     assert CT.sizeof(native.MchParams) == 7 * 8
-    assert CT.sizeof(native.OptimizeDesc) == 10 * 4 + 8 * 3 + 4 * 8 + 56 + 8 + 5 * 8 + 4 * 8
+    assert CT.sizeof(native.OptimizeDesc) == 12 * 4 + 8 * 3 + 4 * 8 + 56 + 8 + 5 * 8 + 4 * 8
     assert CT.sizeof(native.CollapseDesc) == 10 * 4 + 2 * 8 + 3 * 8 + 4 * 8 + 4 * 8 + 2 * 8
 
 
