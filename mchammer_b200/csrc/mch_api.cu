@@ -309,7 +309,8 @@ int mch_optimize_batch(const mch_optimize_desc* d, void* stream) {
                          cluster > 1 ? 512 : auto_threads(d->n_atoms, d->n_chains, smem, d->compute_dtype),
                          d->compute_dtype == MCH_F64 ? 512 : 1024, &threads);
   if (rc != MCH_OK) return rc;
-  if (cluster > 1 && threads < 64) return fail(MCH_ERR_INVALID, "a chain on a cluster needs at least 64 threads per CTA");
+  if (cluster > 1 && (threads < 64 || threads > 512))
+    return fail(MCH_ERR_INVALID, "a chain on a cluster takes 64 to 512 threads per CTA, got %d", threads);
 
   mch::OptArgs a;
   a.pos_in = d->pos_in; a.pos_in_stride = d->pos_in_chain_stride; a.pos_out = d->pos_out;
@@ -326,6 +327,7 @@ int mch_optimize_batch(const mch_optimize_desc* d, void* stream) {
   a.inexact_undo = d->inexact_undo;
   a.defer = defer;
   a.cluster = cluster;
+  a.latency = d->n_chains <= sm_count() ? 1 : 0;
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
   const bool io_f64 = d->io_dtype == MCH_F64;
   return d->compute_dtype == MCH_F64 ? mch::launch_optimize_f64(io_f64, mk, a, threads, smem, s)

@@ -62,7 +62,7 @@ int launch_optimize_nt(int mk, const OptArgs& a, int threads, int smem, cudaStre
 // a chain spread over a.cluster CTAs: the large-block instantiation, cluster-capable
 template <typename T, typename Tio>
 int launch_optimize_cluster(int mk, const OptArgs& a, int threads, int smem, cudaStream_t s) {
-  constexpr int NT = large_block<T>();
+  constexpr int NT = 512;  // latency case: 512 threads at 128 registers in both precisions (no spills in the control section)
   const int blocks = a.C * a.cluster;
   switch (mk) {
     case MU_3: return launch_clustered(mch_optimize_kernel<T, Tio, MU_3, NT, true>, a, blocks, threads, smem, a.cluster, s, "mch_optimize_batch");
@@ -74,6 +74,10 @@ int launch_optimize_cluster(int mk, const OptArgs& a, int threads, int smem, cud
 template <typename T, typename Tio>
 int launch_optimize_io(int mk, const OptArgs& a, int threads, int smem, cudaStream_t s) {
   if (a.cluster > 1) return launch_optimize_cluster<T, Tio>(mk, a, threads, smem, s);
+  // a lone fp32 chain of 129..512 threads: the same instantiation as a cluster of one (128 registers;
+  // the throughput-oriented large block is held to 64 and spills in the control section)
+  if (sizeof(T) == 4 && a.latency && threads > 128 && threads <= 512)
+    return launch_optimize_cluster<T, Tio>(mk, a, threads, smem, s);
   if (sizeof(T) == 4 && threads <= 32) return launch_optimize_nt<T, Tio, 32>(mk, a, threads, smem, s);
   if (sizeof(T) == 4 && threads <= 64) return launch_optimize_nt<T, Tio, 64>(mk, a, threads, smem, s);
   return threads <= small_block<T>() ? launch_optimize_nt<T, Tio, small_block<T>()>(mk, a, threads, smem, s)

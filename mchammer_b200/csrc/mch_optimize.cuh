@@ -69,6 +69,7 @@ struct OptArgs {
   int inexact_undo;          // 1: reproduce (p - v) + v on reject (fp64 parity)
   int defer;                 // 1: deferred control work + second column-sum buffer (see header)
   int cluster;               // CTAs per chain (thread-block cluster; 1 = the chain is one CTA)
+  int latency;               // 1: at most one chain per SM (host hint: prefer the 128-register instantiations)
 };
 
 struct Ctl {

@@ -40,5 +40,5 @@ for prec in ("fp64", "fp32"):
         run("cube1000", m, lb, su, 500, prec, th)
 m, lb, su = synthetic.cuboctahedron_cage()
 for prec in ("fp64", "fp32"):
-    for th in (0, 256, 512) + ((1024,) if prec == "fp32" else ()):
+    for th in (0, 256, 512):
         run("m12l24", m, lb, su, 100, prec, th)
