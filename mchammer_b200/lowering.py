@@ -59,42 +59,58 @@ def lower_topology(
         raise ValueError("bond_pair_ids refers to an atom id outside the molecule")
 
     keys = list(subunits)
-    owner = np.full(n_atoms, -1, dtype=np.int64)
-    members: list[list[int]] = []
-    for index, key in enumerate(keys):
-        ids = [int(a) for a in subunits[key]]
-        if len(ids) == 0:
+    members: list[np.ndarray] = []
+    for key in keys:
+        try:
+            ids = np.fromiter(subunits[key], dtype=np.int64)
+        except (TypeError, ValueError):
+            ids = np.array([int(a) for a in subunits[key]], dtype=np.int64)
+        if ids.size == 0:
             raise ValueError(f"subunit {key!r} has no atoms")
-        for atom in ids:
-            if atom < 0 or atom >= n_atoms:
-                raise ValueError(f"subunit {key!r} refers to atom {atom} outside the molecule")
-            if owner[atom] == index:
-                raise ValueError(f"atom {atom} is listed twice in subunit {key!r}")
-            if owner[atom] != -1:
+        members.append(ids)
+    owner = np.full(n_atoms, -1, dtype=np.int64)
+    flat = np.concatenate(members) if members else np.zeros(0, dtype=np.int64)
+    clean = flat.size == 0 or (flat.min() >= 0 and flat.max() < n_atoms
+                                and np.bincount(flat, minlength=n_atoms).max() <= 1)
+    if clean:  # the usual case: a partition (of a subset) of the atoms
+        owner[flat] = np.repeat(np.arange(len(members)), [m.size for m in members])
+    else:
+        # something is wrong: walk the subunits in the caller's order so that the first offending
+        # atom decides the error, as a per-atom loop would
+        for index, (key, ids) in enumerate(zip(keys, members)):
+            outside = (ids < 0) | (ids >= n_atoms)
+            taken = np.where(outside, -1, owner[np.where(outside, 0, ids)])
+            repeated = np.ones(ids.size, dtype=bool)
+            repeated[np.unique(ids, return_index=True)[1]] = False
+            bad = outside | repeated | (taken != -1)
+            if bad.any():
+                k = int(np.argmax(bad))
+                atom = int(ids[k])
+                if outside[k]:
+                    raise ValueError(f"subunit {key!r} refers to atom {atom} outside the molecule")
+                if repeated[k]:
+                    raise ValueError(f"atom {atom} is listed twice in subunit {key!r}")
                 raise ValueError(
-                    f"atom {atom} is in two subunits ({keys[owner[atom]]!r} and {key!r}); "
+                    f"atom {atom} is in two subunits ({keys[int(taken[k])]!r} and {key!r}); "
                     "overlapping subunits cannot be moved rigidly on the device"
                 )
-            owner[atom] = index
-        members.append(ids)
-    loose = [int(a) for a in np.nonzero(owner < 0)[0]]
-    if loose:
-        members.append(loose)  # static group: never selected, still interacts
+            owner[ids] = index
+    loose = np.nonzero(owner < 0)[0]
+    if loose.size:
+        members.append(loose.astype(np.int64))  # static group: never selected, still interacts
 
     is_h = None
     if elements is not None:
         is_h = np.array([e == "H" for e in elements], dtype=bool)
-        members = [
-            [a for a in ids if not is_h[a]] + [a for a in ids if is_h[a]] for ids in members
-        ]
+        members = [np.concatenate([ids[~is_h[ids]], ids[is_h[ids]]]) for ids in members]
 
-    perm = np.array([a for ids in members for a in ids], dtype=np.int32)
-    sizes = [len(ids) for ids in members]
+    perm = np.concatenate(members).astype(np.int32) if members else np.zeros(0, dtype=np.int32)
+    sizes = [int(ids.size) for ids in members]
     su_offsets = np.concatenate([[0], np.cumsum(sizes)]).astype(np.int32)
     if is_h is None:
         n_heavy = np.array(sizes, dtype=np.int32)
     else:
-        n_heavy = np.array([int(sum(1 for a in ids if not is_h[a])) for ids in members], dtype=np.int32)
+        n_heavy = np.array([int((~is_h[ids]).sum()) for ids in members], dtype=np.int32)
 
     bond_su = np.full((bonds.shape[0], 2), -1, dtype=np.int32)
     n_user = len(keys)

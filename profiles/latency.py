@@ -41,6 +41,12 @@ for name, mol, lb, su, steps in cases:
     t = time.perf_counter(); orc.optimizer_run(mol.get_position_matrix(), lb, su, p, np.random.default_rng(1)); t = time.perf_counter() - t
     print(f"{name:30s} oracle port: {1e3 * t * steps / min(steps, 100):8.2f} ms (scaled from {min(steps, 100)} steps)")
 
+m12, lb12, su12 = synthetic.cuboctahedron_cage()
+for prec in ("fp64", "fp32"):
+    opt = mch.Optimizer(0.25, 1.2, 500, precision=prec)
+    opt.get_result(m12, lb12, su12)
+    print("%-30s %s: get_result %8.2f ms  (one chain on a thread-block cluster, chosen automatically)" % (
+        "M12L24 cage N=5004, 500 steps", prec, 1e3 * best(lambda: opt.get_result(m12, lb12, su12), 3)))
 g = load_golden("collapser_poc")
 mol = mol_of(g)
 coll = mch.Collapser(0.05, 1.2, True)
