@@ -248,6 +248,8 @@ mch_optimize_kernel(const __grid_constant__ OptArgs a) {
   constexpr bool kX2 = kXF && (MCH_F32X2 != 0);  // packed-instruction tile
   constexpr int kRot3 = !(kX2 && (MCH_X2_ROT3 != 0)) ? 0 : (NTMAX <= 64 ? 2 : 1);  // 2: deep row prefetch (128 registers)
   const bool kDefer = a.defer != 0;  // host policy: off when the second buffer would cost a resident chain
+  // re-sum an accepted move's row of E with all warps (coop_row) where warp 0 alone would take long
+  const bool kCoop = nwarps > 1 && ((CL && G > 1) || !kDefer || a.max_su > REGROUP_SMALL);
   Pcg64 rng;  // loaded after step 0 (nothing of the control state is live across the step-0 sweeps)
   rng.hi = rng.lo = rng.inc_hi = rng.inc_lo = 0ULL; rng.has32 = rng.half = 0u;
   double U = 0.0, Unb = 0.0, Ub_trial = 0.0;
@@ -373,24 +375,32 @@ mch_optimize_kernel(const __grid_constant__ OptArgs a) {
     }
     __syncwarp();
   };
-  // Cluster mode.  This CTA's share of the new row `row` of E after an accepted move: sums over the
-  // columns it swept (column range [o_lo, o_hi) of the sweep that excluded `row`), pushed into slot
-  // [parity][rank] of EVERY CTA's epart through distributed shared memory.
-  auto push_partial_row = [&](const T* cs, int row, int parity) {
-    namespace cg = cooperative_groups;
-    cg::cluster_group cluster = cg::this_cluster();
+  // The new row `row` of E after an accepted move, re-summed from the column sums `cs` of the accepted
+  // sweep by ALL warps of the CTA (subunit t goes to warp t mod nwarps) -- used where one warp would
+  // take long over it: large subunits, chains that do not defer, chains on a cluster.
+  //   one CTA : E[row][t] = E[t][row] = scale * sum_{j in t} cs[j]
+  //   cluster : this CTA swept only the column range [o_lo, o_hi) of the sweep that excluded `row`;
+  //             its share of every sum goes into slot [parity][rank] of EVERY CTA's epart through
+  //             distributed shared memory (summed in rank order by install_partial_rows).
+  auto coop_row = [&](const T* cs, int row, int parity) {
     const int g0 = suoff[row], g1 = suoff[row + 1];
-    int o_lo, o_hi;
-    sweep_part_columns(N - (g1 - g0), rank, G, o_lo, o_hi);
-    for (int t = 0; t < S; ++t) {
+    int o_lo = 0, o_hi = N;
+    if (CL && G > 1) sweep_part_columns(N - (g1 - g0), rank, G, o_lo, o_hi);
+    for (int t = warp; t < S; t += nwarps) {
       double v = 0.0;
       if (t != row) {
-        const int shift = t > row ? (g1 - g0) : 0;  // slot = column + shift (columns skip the gap)
-        const int j_lo = max(suoff[t], o_lo + shift), j_hi = min(suoff[t + 1], o_hi + shift);
+        const int shift = (CL && G > 1 && t > row) ? (g1 - g0) : 0;  // slot = column + shift (columns skip the gap)
+        const int j_lo = (CL && G > 1) ? max(suoff[t], o_lo + shift) : suoff[t];
+        const int j_hi = (CL && G > 1) ? min(suoff[t + 1], o_hi + shift) : suoff[t + 1];
         for (int j = j_lo + lane; j < j_hi; j += 32) v += (double)cs[j];
         v = warp_sum(v) * scale;
       }
-      if (lane < G) cluster.map_shared_rank(epart, lane)[(parity * kMaxCluster + rank) * S + t] = v;
+      if (CL && G > 1) {
+        if (lane < G)
+          cooperative_groups::this_cluster().map_shared_rank(epart, lane)[(parity * kMaxCluster + rank) * S + t] = v;
+      } else if (lane == 0 && t != row) {
+        E[row * S + t] = v; E[t * S + row] = v;
+      }
     }
   };
   auto install_partial_rows = [&](int row, int parity) {  // E[row][t] = sum over CTAs, rank order
@@ -517,6 +527,7 @@ mch_optimize_kernel(const __grid_constant__ OptArgs a) {
     double longest;
     U = Unb + bond_terms(-1, (T)0, (T)0, (T)0, longest);
     info = -1;
+    if (lane == 0) { ctl->d_accepted = 0; ctl->d_ms = 0; }
     write_trace(0, longest);
     if (a.num_steps <= 1 && lane == 0 && rank == 0) a.maxd[c] = longest;
     __syncwarp();
@@ -538,6 +549,10 @@ mch_optimize_kernel(const __grid_constant__ OptArgs a) {
         store_io<Tio>(a.traj, dst + 2, (double)Z[n] + ctl->origin[2]);
       }
     }
+    if (kCoop && ctl->d_accepted != 0) {  // uniform over the CTA: published by warp 0 before barrier A
+      coop_row(colsum + (kDefer ? ((step - 1) & 1) : 0) * colsum_stride, ctl->d_ms, step & 1);
+      __syncthreads();
+    }
     if (warp == 0) {
       // DEFERRED half of the control work, overlapped with the other warps' sweep:
       // (1) the previous move was accepted -> rebuild row/column d_ms of the energy table
@@ -546,10 +561,9 @@ mch_optimize_kernel(const __grid_constant__ OptArgs a) {
       if (kDefer) {
         if (d_accepted) {
           if (CL && G > 1) {
-            // this CTA's share of the new row goes to every CTA; installed after this step's cluster barrier
-            push_partial_row(colsum + d_buf * colsum_stride, d_ms, step & 1);
+            // coop_row pushed this CTA's share to every CTA; installed after this step's cluster barrier
           } else {
-            regroup(colsum + d_buf * colsum_stride, d_ms, 0);
+            if (!kCoop) regroup(colsum + d_buf * colsum_stride, d_ms, 0);
             refresh_erow();
             d_accepted = false;
           }
@@ -561,6 +575,9 @@ mch_optimize_kernel(const __grid_constant__ OptArgs a) {
         }
         double unused;
         Ub_trial = bond_terms(ms, tvx, tvy, tvz, unused);
+      } else if (kCoop && d_accepted) {
+        refresh_erow();
+        d_accepted = false;
       }
       park();
     }
@@ -637,9 +654,12 @@ mch_optimize_kernel(const __grid_constant__ OptArgs a) {
       __syncwarp();
       info = kb | ((ok ? 1 : 0) << 16) | (kind << 17) | (ms << 18);
       d_accepted = ok; d_ms = ms; d_buf = kDefer ? (step & 1) : 0; d_step = step;
+      if (kCoop && lane == 0) { ctl->d_accepted = ok ? 1 : 0; ctl->d_ms = ms; }  // for coop_row after barrier A
       if (!kDefer) {
-        if (ok) { regroup(colsum + d_buf * colsum_stride, ms, 0); refresh_erow(); }
-        d_accepted = false;
+        if (!kCoop) {
+          if (ok) { regroup(colsum + d_buf * colsum_stride, ms, 0); refresh_erow(); }
+          d_accepted = false;
+        }
         if (step + 1 < a.num_steps && (a.trace_f || a.trace_i)) {
           double longest = 0.0;
           if (a.trace_f) (void)bond_terms(-1, (T)0, (T)0, (T)0, longest);
