@@ -285,9 +285,9 @@ int mch_optimize_batch(const mch_optimize_desc* d, void* stream) {
     return fail(MCH_ERR_INVALID, "mch_optimize_batch: cluster_size must be 0 (auto), 1, 2, 4 or 8, got %d", cluster);
   if (cluster == 0) {
     cluster = 1;
-    if (d->n_atoms >= 2048 && d->num_steps > 1) {
+    if (d->n_atoms >= 768 && d->num_steps > 1) {  // measured: profiles/r01_cluster_chain.txt
       const int sms = sm_count();
-      for (int g = 8; g >= 2; g /= 2)
+      for (int g = d->n_atoms >= 2048 ? 8 : 4; g >= 2; g /= 2)
         if ((long long)d->n_chains * g <= sms) {
           int defer_unused;
           if (plan_chain_smem(d->n_atoms, d->n_subunits, d->n_bonds, d->max_subunit_atoms, d->compute_dtype,

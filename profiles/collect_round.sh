@@ -30,5 +30,12 @@ if python bench.py --steps 2 --warmup 1 --no-cpu-baseline --precision fp64 > /de
   ncu --set full --clock-control none --import-source on -k regex:mch_optimize -c 1 -f -o $O/${R}_full_fp64 \
       python bench.py --steps 2 --warmup 1 --no-cpu-baseline --precision fp64 > $O/${R}_ncu_full_fp64.log 2>&1
 fi
+# summarise the full captures here and drop the reports (gpurun merges back at most 64 MiB)
+for k in fp32 fp64; do
+  if [ -f $O/${R}_full_$k.ncu-rep ]; then
+    python profiles/ncu_summary.py $O/${R}_full_$k.ncu-rep --json $O/${R}_ncu_full_$k.json > $O/${R}_ncu_full_$k.txt 2>&1
+    rm -f $O/${R}_full_$k.ncu-rep
+  fi
+done
 tail -2 $O/${R}_pytest_gpu.txt
 cat $O/${R}_bench.json | python profiles/bench_line.py
