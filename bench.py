@@ -49,6 +49,7 @@ def parse_args():
     ap.add_argument("--num-steps", type=int, default=0, help="Optimizer num_steps (default: workload's)")
     ap.add_argument("--threads", type=int, default=0, help="threads per chain (0 = library default)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-secondary", action="store_true", help="skip the fp64 / M12L24 / strong-scaling lines")
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="CPU baseline budget per core")
     ap.add_argument("--cpu-worker", action="store_true", help=argparse.SUPPRESS)
     ap.add_argument("--cpu-moves", type=int, default=0, help=argparse.SUPPRESS)
@@ -65,31 +66,57 @@ def build_workload(name: str):
 
 
 # =====================================================================================
-# CPU arm: the oracle port (oracle/mch_oracle.py) on the host cores, one chain per process
+# CPU arm: the UNMODIFIED reference (baseline/_ref, `pip install --target` of /root/reference,
+# see DESIGN.md section 7) when it is on this box, else the oracle port (oracle/mch_oracle.py,
+# labelled "port") -- one chain per process on all host cores either way
 # =====================================================================================
+REF_DIR = os.path.join(REPO, "baseline", "_ref")
+
+
+def reference_available() -> bool:
+    return os.path.isfile(os.path.join(REF_DIR, "mchammer", "__init__.py"))
+
+
 def _cpu_chain(job):
-    """One chain of `moves` Monte-Carlo moves through the oracle; returns seconds."""
+    """One chain of `moves` Monte-Carlo moves on the CPU; returns seconds."""
     import numpy as np
 
+    kind, elements, bonds, pos, long_bonds, subunits, moves, seed = job
+    if kind == "reference":
+        if REF_DIR not in sys.path:
+            sys.path.insert(0, REF_DIR)
+        import mchammer as ref  # the unmodified reference package
+
+        mol = ref.Molecule(
+            atoms=tuple(ref.Atom(id=i, element_string=e) for i, e in enumerate(elements)),
+            bonds=tuple(ref.Bond(id=i, atom_ids=b) for i, b in enumerate(bonds)),
+            position_matrix=pos,
+        )
+        opt = ref.Optimizer(step_size=0.25, target_bond_length=1.2, num_steps=moves + 1, random_seed=seed)
+        t0 = time.perf_counter()
+        opt.get_result(mol, long_bonds, subunits)
+        return time.perf_counter() - t0
     from oracle import mch_oracle as orc
 
-    pos, long_bonds, subunits, moves, seed = job
     p = orc.OptimizerParams(step_size=0.25, target_bond_length=1.2, num_steps=moves + 1)
     t0 = time.perf_counter()
     orc.optimizer_run(pos, long_bonds, subunits, p, np.random.default_rng(seed))
     return time.perf_counter() - t0
 
 
-def cpu_sample(workload: str, moves: int, chains: int, cores: int):
-    """Run `chains` oracle chains of `moves` moves over `cores` processes; wall seconds."""
+def cpu_sample(workload: str, moves: int, chains: int, cores: int, kind: str):
+    """Run `chains` CPU chains of `moves` moves over `cores` processes; wall seconds."""
     import multiprocessing as mp
 
     mol, long_bonds, subunits = build_workload(workload)
     pos = mol.get_position_matrix()
-    jobs = [(pos, long_bonds, subunits, moves, 1000 + c) for c in range(chains)]
+    elements = [a.get_element_string() for a in mol.get_atoms()]
+    bonds = [(b.get_atom1_id(), b.get_atom2_id()) for b in mol.get_bonds()]
+    jobs = [(kind, elements, bonds, pos, long_bonds, subunits, moves, 1000 + c) for c in range(chains)]
     ctx = mp.get_context("fork")
     with ctx.Pool(processes=cores) as pool:
-        pool.map(_cpu_chain, jobs[:cores])  # warm the workers (imports, first-call costs)
+        warm = [(kind, elements, bonds, pos, long_bonds, subunits, 2, 1) for _ in range(cores)]
+        pool.map(_cpu_chain, warm)  # warm the workers (imports, first-call costs)
         t0 = time.perf_counter()
         per_chain = pool.map(_cpu_chain, jobs, chunksize=1)
         wall = time.perf_counter() - t0
@@ -99,8 +126,9 @@ def cpu_sample(workload: str, moves: int, chains: int, cores: int):
 def cpu_worker_main(args):
     """Child process entry (never imports torch, so fork() is safe)."""
     cores = os.cpu_count() or 1
-    wall, busy = cpu_sample(args.workload, args.cpu_moves, args.cpu_chains, cores)
-    print(json.dumps({"wall": wall, "busy": busy, "cores": cores}))
+    kind = "reference" if reference_available() else "port"
+    wall, busy = cpu_sample(args.workload, args.cpu_moves, args.cpu_chains, cores, kind)
+    print(json.dumps({"wall": wall, "busy": busy, "cores": cores, "kind": kind}))
 
 
 def run_cpu_subprocess(workload: str, moves: int, chains: int):
@@ -113,8 +141,15 @@ def run_cpu_subprocess(workload: str, moves: int, chains: int):
     return json.loads(out.stdout.strip().splitlines()[-1])
 
 
+def _cpu_what(kind: str) -> str:
+    if kind == "reference":
+        return ("the unmodified reference (mchammer.Optimizer.get_result imported from baseline/_ref, "
+                "pure Python + numpy/scipy)")
+    return "oracle/mch_oracle.py (numpy/scipy restatement of the reference; baseline/_ref absent on this box)"
+
+
 def cpu_baseline(workload: str, budget_s: float):
-    """Oracle port on all host cores, bounded to about `budget_s` seconds per core."""
+    """The CPU path on all host cores, bounded to about `budget_s` seconds per core."""
     cores = os.cpu_count() or 1
     n_atoms = 1000 if workload == "cube1000" else 5004
     est_move_s = 1.0e-2 * (n_atoms / 1000.0) ** 2  # ~100 moves/s/core at N = 1000 (BASELINE.md)
@@ -123,9 +158,9 @@ def cpu_baseline(workload: str, budget_s: float):
     r = run_cpu_subprocess(workload, moves, chains)
     value = chains * moves / r["wall"]
     return {
-        "value": value, "unit": UNIT, "cores": r["cores"], "kind": "port",
-        "sample": f"{chains} chains x {moves} moves of {workload} through oracle/mch_oracle.py "
-                  f"(numpy/scipy restatement of the reference), one chain per process on {r['cores']} cores, "
+        "value": value, "unit": UNIT, "cores": r["cores"], "kind": r["kind"],
+        "sample": f"{chains} chains x {moves} moves of {workload} through {_cpu_what(r['kind'])}, "
+                  f"one chain per process on {r['cores']} cores, "
                   f"{r['wall']:.1f} s wall; per-core rate {chains * moves / r['busy']:.1f} chain-steps/s",
     }
 
@@ -141,14 +176,15 @@ def reference_arm(args):
     moves = max(3, int(1.0 / est_move_s))  # ~1 s of work per chain per bench step
     chains = cores
     total = args.steps + args.warmup
-    times = []
+    times, kind = [], "port"
     for k in range(total):
         r = run_cpu_subprocess(args.workload, moves, chains)
+        kind = r["kind"]
         if k >= args.warmup:
             times.append(r["wall"])
     seconds = sum(times)
     value = args.steps * chains * moves / seconds
-    sample = (f"each step = {chains} chains x {moves} moves of {args.workload} through the oracle port, "
+    sample = (f"each step = {chains} chains x {moves} moves of {args.workload} through {_cpu_what(kind)}, "
               f"one chain per process on {cores} cores")
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
@@ -157,7 +193,7 @@ def reference_arm(args):
         "data": "synthetic",
         "config": {"workload": f"{args.workload}: {spec['chains']} chains/GPU x {spec['num_steps']} num_steps "
                                "(CPU arm runs a bounded sample of it)", "sample": sample},
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -243,27 +279,113 @@ def profiled_traffic(precision: str):
 
 
 def probe_pipe_peak(torch, dtype_code: int, device) -> float:
-    """TFLOP/s of a pure dependent-FMA kernel (8 chains/thread) -- the arithmetic-pipe roofline."""
-    import ctypes as C
+    """TFLOP/s of a pure dependent-FMA kernel (8 chains/thread) -- the arithmetic-pipe roofline.
+    The probe kernels live in the bench-only library profiles/probes (not in the product ABI)."""
+    from profiles import probes
 
-    from mchammer_b200 import native
+    return probes.pipe_peak(torch, dtype_code, device)
 
-    lib = native.lib()
-    sink = torch.zeros(1, dtype=torch.float32, device=device)
-    blocks, threads, iters = 148 * 8, 256, 1 << 15
-    stream = torch.cuda.current_stream(device).cuda_stream
-    best = 0.0
-    for _ in range(4):
+
+def time_resident(torch, dist, device, launch, n_timed: int, flush) -> float:
+    """Seconds of `n_timed` launches (CUDA events around each, L2 flushed in between, one
+    untimed warm-up launch first), MAX over ranks."""
+    launch()
+    torch.cuda.synchronize()
+    if dist is not None:
+        dist.barrier()
+    events = []
+    for _ in range(n_timed):
+        flush.zero_()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        native.check(lib.mch_probe_fma(dtype_code, blocks, threads, iters, C.c_void_p(sink.data_ptr()),
-                                       C.c_void_p(stream)), "mch_probe_fma")
+        launch()
         e1.record()
-        e1.synchronize()
-        ms = e0.elapsed_time(e1)
-        per_op = {2: 1.0, 3: 4.0}.get(dtype_code, 2.0)  # MUFU: results; FFMA2: 2 lanes x 2 flops
-        best = max(best, per_op * 8.0 * iters * blocks * threads / (ms * 1e-3) / 1e12)
-    return best
+        events.append((e0, e1))
+    torch.cuda.synchronize()
+    seconds = sum(a.elapsed_time(b) for a, b in events) * 1e-3
+    if dist is not None:
+        t = torch.tensor([seconds], dtype=torch.float64, device=device)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        seconds = float(t[0])
+    return seconds
+
+
+def secondary_lines(torch, dist, device, world: int, rank: int, flush, main_value: float, main_chains: int):
+    """The other numbers BASELINE.json's metric names, measured in this same run, device resident,
+    CUDA events, max over ranks (every rank runs them; rank 0 reports):
+      fp64         parity mode on the headline workload (cube1000, 4096 chains/GPU, num_steps 500)
+      m12l24_fp32  BASELINE configs[4] geometry, 1024 chains/GPU (8192/GPU on 8 GPUs = the 65,536-chain batch)
+      strong_4096  the FIXED 4096-chain cube1000 batch split over the ranks (strong scaling)
+    """
+    import mchammer_b200 as mch
+    from mchammer_b200 import engine, native, rngstate, synthetic
+    from mchammer_b200.lowering import lower_topology
+
+    def resident(workload, chains, num_steps, precision, n_timed):
+        mol, long_bonds, subunits = build_workload(workload)
+        opt = mch.Optimizer(step_size=0.25, target_bond_length=1.2, num_steps=num_steps, precision=precision,
+                            device=device.index)
+        topo = lower_topology(mol.get_num_atoms(), long_bonds, subunits)
+        dtopo = engine.upload_topology(topo, device.index)
+        pos = torch.from_numpy(mol.get_position_matrix()).to(device)
+        words = rngstate.seed_states([1000 + rank * chains + c for c in range(chains)])
+        rng0 = engine.rng_words_to_device(words, device)
+        rng = rng0.clone()
+        state = {"out": None}
+
+        def launch():
+            rng.copy_(rng0)
+            state["out"] = engine.optimize_on_device(dtopo, pos, chains, rng, opt._params(), num_steps, precision,
+                                                     out=state["out"])
+
+        seconds = time_resident(torch, dist, device, launch, n_timed, flush)
+        pairs = int(state["out"].pair_evals.sum().item())
+        return seconds / n_timed, pairs, mol.get_num_atoms()
+
+    out = {}
+    # --- fp64 parity mode on the headline workload
+    chains, num_steps = WORKLOADS["cube1000"]["chains"], WORKLOADS["cube1000"]["num_steps"]
+    sec, pairs, n_atoms = resident("cube1000", chains, num_steps, "fp64", 2)
+    peak64 = probe_pipe_peak(torch, native.MCH_F64, device) if rank == 0 else None
+    ach = FLOPS_PER_PAIR * pairs / sec / 1e12
+    out["fp64"] = {
+        "workload": f"cube1000: {chains} chains/GPU x {n_atoms} atoms, num_steps={num_steps}, parity mode",
+        "value": chains * world * (num_steps - 1) / sec, "unit": UNIT, "ms_per_launch": 1e3 * sec,
+        "pair_evals_per_s": pairs * world / sec,
+        "roofline": {"bound": "fp64_pipe", "achieved": ach, "peak": peak64, "unit": "TFLOP/s",
+                     "frac": ach / peak64 if peak64 else None},
+    }
+    # --- M12L24 (BASELINE configs[4]): 65,536 chains over 8 GPUs = 8192 per GPU; 1024 per GPU otherwise
+    m_chains = 8192 if world == 8 else 1024
+    m_steps = WORKLOADS["m12l24"]["num_steps"]
+    sec, pairs, n_atoms = resident("m12l24", m_chains, m_steps, "fp32", 2)
+    peak32 = None
+    if rank == 0:
+        peak32 = max(probe_pipe_peak(torch, native.MCH_F32, device), probe_pipe_peak(torch, 3, device))
+    ach = FLOPS_PER_PAIR * pairs / sec / 1e12
+    out["m12l24_fp32"] = {
+        "workload": f"m12l24: {m_chains} chains/GPU x {n_atoms} atoms ({m_chains * world} chains in all), "
+                    f"num_steps={m_steps} (reduced from 500, BASELINE configs[4] allows it), fast mode",
+        "value": m_chains * world * (m_steps - 1) / sec, "unit": UNIT, "ms_per_launch": 1e3 * sec,
+        "pair_evals_per_s": pairs * world / sec,
+        "roofline": {"bound": "fp32_pipe", "achieved": ach, "peak": peak32, "unit": "TFLOP/s",
+                     "frac": ach / peak32 if peak32 else None},
+    }
+    # --- strong scaling: the fixed 4096-chain batch over all ranks
+    total = 4096
+    num_steps = WORKLOADS["cube1000"]["num_steps"]
+    if world == 1 and main_chains == total:
+        value, ms = main_value, None
+    else:
+        per = total // world
+        sec, _, _ = resident("cube1000", per, num_steps, "fp32", 5)
+        value, ms = per * world * (num_steps - 1) / sec, 1e3 * sec
+    out["strong_4096"] = {
+        "workload": f"cube1000: {total} chains in all = {total // world} per GPU, num_steps={num_steps}, fast mode",
+        "value": value, "unit": UNIT, "ms_per_launch": ms, "scaling": "strong",
+        "note": "efficiency = value / (n_gpus x the 1-GPU value of this same line)",
+    }
+    return out
 
 
 def cuda_arm(args):
@@ -345,6 +467,22 @@ def cuda_arm(args):
     clocks = sampler.stop(t_begin, time.perf_counter())
     accepted = float(res.n_accepted.mean())
 
+    # ---------------- the cold public call: seeds in, results out, nothing prepared
+    # (plan allocation + pinning + numpy-compatible seeding + copies + kernel + result copy)
+    cold_t0 = time.perf_counter()
+    cold = opt.get_results_batch(mol, long_bonds, subunits, seeds=seeds, devices=[local])
+    cold_seconds = time.perf_counter() - cold_t0
+    cold_ok = bool(np.array_equal(cold.n_accepted, res.n_accepted))
+    del cold
+
+    # ---------------- the other configurations the metric names (fp64, M12L24, strong scaling)
+    secondary = None
+    if not args.no_secondary and args.workload == "cube1000" and args.precision == "fp32":
+        del plan, res
+        torch.cuda.empty_cache()
+        secondary = secondary_lines(torch, dist, device, world, rank, flush,
+                                    args.steps * chains * moves / dev_seconds, chains)
+
     # ---------------- reduce over ranks: slowest rank sets the time
     if dist is not None:
         t = torch.tensor([dev_seconds, e2e_seconds], dtype=torch.float64, device=device)
@@ -397,7 +535,13 @@ def cuda_arm(args):
             },
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "api": "Optimizer.prepare_batch(...).run(rng_words, positions) with pinned host buffers; "
-                           "the call pipelines H2D / kernel / D2H over 4 slices of the batch"},
+                           "the call pipelines H2D / kernel / D2H over 4 slices of the batch",
+                    "cold_public_call": {
+                        "api": "Optimizer.get_results_batch(mol, bonds, subunits, seeds): plan allocation + pinning + "
+                               "PCG64 seeding + H2D + kernel + D2H + result copy, one call per rank on its own GPU (rank 0's time)",
+                        "seconds": cold_seconds, "value": chains * moves / cold_seconds, "unit": UNIT,
+                        "same_accept_counts_as_prepared_plan": cold_ok}},
+            "secondary": secondary,
             "gpu_launches": args.steps,
             "gpu_launches_e2e": args.steps * gpu_launches_e2e,
             "clocks": clocks,

@@ -65,7 +65,9 @@ typedef struct mch_optimize_desc {
   int32_t inexact_undo;       /* 1: on reject redo (p - v) + v like optimizer.py:273-277 */
   int32_t threads_per_chain;  /* 0 = auto; else multiple of 32, <= 1024 (fp32) / 512 (fp64) */
   int32_t cluster_size;       /* CTAs (SMs) per chain: 0 = auto, 1 = one CTA, 2 / 4 / 8 = thread-block cluster */
-  int32_t reserved;           /* 0                                                      */
+  int32_t resident_chains_hint; /* 0, or the number of chains of the whole batch when the caller cuts one batch
+                                 into several launches that run concurrently (pipelined slices): block size,
+                                 cluster and occupancy choices are then made for the batch, not per slice */
   const void* pos_in;         /* [dev] [n_chains or 1][n_atoms][3]                        */
   int64_t pos_in_chain_stride;/* elements between chains; 0 = all chains start from chain 0 */
   void* pos_out;              /* [dev] [n_chains][n_atoms][3]                             */
@@ -117,6 +119,10 @@ typedef struct mch_collapse_desc {
   int32_t max_steps;          /* safety cap; status 1 when reached                        */
   int32_t trace_capacity;     /* steps the trace/trajectory buffers can hold              */
   int32_t threads_per_mol;    /* 0 = auto                                                 */
+  int32_t n_moving_subunits;  /* the first n_moving_subunits subunits are the caller's dict entries; a trailing
+                                 group (atoms in no subunit) never moves, is not contact-tested and does not
+                                 enter the step scales (collapser.py:56-82, :106-157).  0 = all n_subunits */
+  int32_t reserved;           /* 0                                                        */
   double step_size, distance_threshold;
   const void* pos_in;         /* [dev] [n_mol or 1][n_atoms][3]                           */
   int64_t pos_in_mol_stride;
@@ -147,20 +153,6 @@ int mch_pcg64_seed(const uint64_t* seeds, int n, uint64_t* rng_state_out);
 int mch_pcg64_stream_check(uint64_t* rng_state /* [6] in/out */, int rounds, uint32_t bound,
                            int64_t* ints_out /* [3*rounds] */,
                            double* doubles_out /* [rounds + (rounds+2)/3] */);
-
-/* Arithmetic-pipe probe for the roofline denominators: every thread runs `iters` rounds of
- * 8 independent FMAs in `dtype` (0 = f64, 1 = f32; 2 = 8 f32 MUFU.RSQ instead);
- * 2*8*iters*blocks*threads flops per launch.  dtype 3..7 are issue-mix probes of 8 (mode 6:
- * 14) instructions per round -- 3: 8 FFMA2, 4: 6 FFMA2 + 2 MUFU.RSQ, 5: 6 FFMA + 2 MUFU.RSQ,
- * 6: 12 FFMA + 2 MUFU.RSQ, 7: mode 4 with one broadcast LDS.128 -- read by profiles/probe_mix.py. */
-int mch_probe_fma(int dtype, int blocks, int threads, int iters, float* sink /* [dev] [1] */,
-                  void* stream);
-
-/* Ceiling probe for the fp32 pair sweep: every CTA runs `iters` sweeps of n_rows x n_cols pair
- * terms (the Monte-Carlo kernel's inner tile loop, no control section); with_barrier adds the
- * per-sweep __syncthreads().  n_rows*n_cols*iters*blocks pair terms per launch. */
-int mch_probe_sweep(int blocks, int threads, int iters, int with_barrier, int n_rows, int n_cols,
-                    float* sink /* [dev] [1] */, void* stream);
 
 const char* mch_last_error(void);
 int mch_version(void);

@@ -274,6 +274,7 @@ class BatchPlan:
                         o = engine.optimize_on_device(
                             sh.dtopo, pos, hi - lo, sh.rng[lo:hi], self.params, self.num_steps,
                             self.precision, threads_per_chain=self.threads_per_chain, out=sh.out_slice(lo, hi),
+                            resident_chains_hint=sh.count,  # the slices run concurrently: choices are the batch's
                         )
                         self.h_pos_out[g_lo:g_hi].copy_(o.positions, non_blocking=True)
                         self.h_f64[0, g_lo:g_hi].copy_(o.system_potential, non_blocking=True)
@@ -356,7 +357,7 @@ class BatchPlan:
                         o.trajectory = buf["traj"][:m] if want_positions else None
                         engine.optimize_on_device(
                             sh.dtopo, pos, m, sh.rng[lo:hi], self.params, steps, self.precision,
-                            threads_per_chain=self.threads_per_chain, out=o,
+                            threads_per_chain=self.threads_per_chain, out=o, resident_chains_hint=sh.count,
                         )
                         if want_positions:
                             h_traj[g_lo:g_hi].copy_(o.trajectory, non_blocking=True)

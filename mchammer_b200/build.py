@@ -17,6 +17,10 @@ import sys
 PKG = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(PKG, "csrc")
 LIB = os.path.join(PKG, "libmchammer_b200.so")
+# bench-only measurement kernels (roofline denominators, sweep-only ceiling): their own library
+PROBES_DIR = os.path.join(os.path.dirname(PKG), "profiles", "probes")
+PROBES_SRC = os.path.join(PROBES_DIR, "mch_probes.cu")
+PROBES_LIB = os.path.join(PROBES_DIR, "libmch_probes.so")
 SOURCES = ["mch_api.cu", "mch_optimize_f32.cu", "mch_optimize_f64.cu"]
 HEADERS = [
     "mch_device.cuh", "mch_optimize.cuh", "mch_potential.cuh", "mch_collapse.cuh", "mch_host.h",
@@ -80,9 +84,25 @@ def build_library(force: bool = False, verbose: bool = False, defines=(), out: s
     return target
 
 
+def build_probes(force: bool = False, defines=(), out: str | None = None) -> str:
+    """profiles/probes/mch_probes.cu -> libmch_probes.so (bench-only; includes the product's device headers)."""
+    target = out or PROBES_LIB
+    deps = [PROBES_SRC, os.path.join(CSRC, "mch_device.cuh")]
+    if (out is None and not defines and not force and os.path.exists(target)
+            and all(os.path.getmtime(d) <= os.path.getmtime(target) for d in deps)):
+        return target
+    cmd = [_nvcc(), *NVCC_FLAGS, *[f"-D{d}" for d in defines], "-shared", "-o", target, PROBES_SRC]
+    proc = subprocess.run(cmd, capture_output=True, text=True)
+    if proc.returncode != 0:
+        raise RuntimeError("nvcc failed:\n" + " ".join(cmd) + "\n" + proc.stdout + proc.stderr)
+    return target
+
+
 if __name__ == "__main__":
     defs = [a[2:] for a in sys.argv[1:] if a.startswith("-D")]
     outs = [a[6:] for a in sys.argv[1:] if a.startswith("--out=")]
     path = build_library(force="--force" in sys.argv, verbose="-v" in sys.argv, defines=defs,
                          out=outs[0] if outs else None)
     print(path)
+    if not outs:
+        print(build_probes(force="--force" in sys.argv))

@@ -59,6 +59,7 @@ class Collapser:
         self._precision = precision
         self._device = device
         self._max_steps = int(max_steps)
+        self._trace_capacity_guess = 64  # steps get_trajectory records in its first launch
 
     # ------------------------------------------------------------------ host conveniences
     def _get_subunit_distances(self, mol: Molecule, subunits: dict) -> Iterator[float]:
@@ -154,17 +155,18 @@ class Collapser:
         )
         result.update_log(rule + " " * 17 + "Running optimisation!" + " " * 14 + "\n" + rule + "\n")
 
-        # the loop length is data dependent: a first (cheap, deterministic) run sizes the
-        # trajectory buffers, the second fills them
+        # the loop length is data dependent: the trace buffers are sized by a guess and the launch is
+        # repeated only if the loop ran longer (the kernel records the first `trace_capacity` steps
+        # and keeps counting)
         coords = mol.get_position_matrix()
-        probe = self._run(mol, coords, bond_pair_ids, subunits, 1)
-        steps = int(probe.steps_run.item())
-        out = probe
+        capacity = self._trace_capacity_guess
+        out = self._run(mol, coords, bond_pair_ids, subunits, 1, trace_capacity=capacity, want_trajectory=True)
+        steps = int(out.steps_run.item())
+        if steps > capacity:
+            out = self._run(mol, coords, bond_pair_ids, subunits, 1, trace_capacity=steps, want_trajectory=True)
         if steps > 0:
-            out = self._run(mol, coords, bond_pair_ids, subunits, 1, trace_capacity=steps,
-                            want_trajectory=True)
-            far = out.trace_max_bond[0].cpu().numpy()
-            frames = out.trajectory[0].cpu().numpy().astype(np.float64)
+            far = out.trace_max_bond[0, :steps].cpu().numpy()
+            frames = out.trajectory[0, :steps].cpu().numpy().astype(np.float64)
             for k in range(steps):
                 result.add_step_result(
                     StepResult(step=k + 1, position_matrix=frames[k],

@@ -31,10 +31,6 @@ int fail(int code, const char* fmt, ...) {
 namespace {
 using mch::fail;
 using mch::launch;
-using mch::f32x2;
-using mch::pack2;
-using mch::unpack2;
-using mch::fma2;
 
 constexpr int kMaxSmem = 227 * 1024;
 
@@ -62,11 +58,6 @@ int mu_kind(double mu, int* mu_int) {
   return mch::MU_REAL;
 }
 
-// Threads per chain when the caller does not say.  Measured on B200:
-// chains that share an SM run best with few warps each -- every warp of a chain but one
-// idles while the chain's control section runs, and with one or two warps per chain that
-// loss (almost) disappears while 8-10 resident chains still keep the pipes busy.  Large
-// molecules (one or two chains per SM) get 16 / 8 warps per chain instead.
 int sm_count() {  // SMs of the current device (queried once per device)
   static int cache[64] = {0};
   int dev = 0;
@@ -78,22 +69,28 @@ int sm_count() {  // SMs of the current device (queried once per device)
   return cache[dev];
 }
 
-// Block size when the caller leaves it open.  Batches that fill the GPU: few warps per chain
-// and as many resident chains as shared memory allows (measured best).
-// At most one chain per SM (the single-molecule drop-in calls): nothing else hides the
-// chain's latency, so it gets up to 16 warps (profiles/single_chain_kernel.py: a 1000-atom
-// chain 16.7 -> 9.7 us per step in fp64, 8.1 -> 5.3 in fp32).
-int auto_threads(int n_atoms, int n_chains, int smem_bytes, int compute_dtype) {
-  if (n_chains <= sm_count()) {
-    if (n_atoms <= 128) return compute_dtype == MCH_F64 ? 128 : 32;
-    const int t = ((n_atoms / 2 + 31) / 32) * 32;
-    return t < 128 ? 128 : (t > 512 ? 512 : t);
-  }
-  if (n_atoms <= 128) return 32;
-  const int chains_per_sm = kMaxSmem / smem_bytes;
-  if (chains_per_sm >= 3) return compute_dtype == MCH_F64 ? 128 : 64;
-  // two chains per SM: fill the register file (fp32: 2 x 512 x 64, fp64: 2 x 256 x 128)
-  return chains_per_sm == 2 && compute_dtype == MCH_F64 ? 256 : 512;
+// Block size when the caller leaves it open (measured: DESIGN.md section 8, profiles/r02_chain_sweep*.txt).
+//   per_sm  = chains that will share an SM = min(chains that fit its shared memory, ceil(batch / SMs))
+//   by_smem = chains that fit an SM's shared memory
+// A batch that fills the GPU runs best with few warps per chain and as many resident chains as
+// shared memory allows: every warp of a chain but one idles while the chain's serial control
+// section runs, and with two warps per chain that loss (almost) disappears while eight resident
+// chains keep the pipes busy.  A batch that leaves room (fewer chains per SM than would fit) is
+// bound by the latency of a chain instead, so every chain gets the share of the SM's register
+// file its neighbours leave it -- 512 / per_sm threads at 128 registers -- up to the point where
+// more warps have no column units left to work on.  Molecules of which only two chains fit an SM
+// (M12L24) fill the register file in fp32 with 2 x 512 threads at 64 registers (*regs64).
+int auto_threads(int n_atoms, int per_sm, int by_smem, int compute_dtype, bool* regs64) {
+  *regs64 = false;
+  const bool f64 = compute_dtype == MCH_F64;
+  if (n_atoms <= 128) return (per_sm <= 1 && f64) ? 128 : 32;
+  int useful = ((n_atoms / 2 + 31) / 32) * 32;  // about one 64-column unit per warp
+  useful = useful < 128 ? 128 : (useful > 512 ? 512 : useful);
+  if (!f64 && by_smem == 2 && per_sm == 2) { *regs64 = true; return 512; }
+  int t = (512 / per_sm) / 32 * 32;
+  const int floor_t = f64 ? 128 : 64;
+  t = t < floor_t ? floor_t : t;
+  return t < useful ? t : useful;
 }
 
 int check_threads(int requested, int fallback, int limit, int* out) {
@@ -114,78 +111,6 @@ int launch_potential_mu(int mk, const mch::PotArgs& a, int threads, int smem, cu
 }
 
 bool dtype_ok(int d) { return d == MCH_F64 || d == MCH_F32; }
-
-// ------------------------------------------------------------------ arithmetic probes
-template <typename T>
-__global__ void probe_fma_kernel(int iters, float* sink) {
-  T a0 = (T)threadIdx.x * (T)1e-3, a1 = a0 + (T)1, a2 = a0 + (T)2, a3 = a0 + (T)3;
-  T a4 = a0 + (T)4, a5 = a0 + (T)5, a6 = a0 + (T)6, a7 = a0 + (T)7;
-  const T m = (T)0.999, c = (T)1e-3;
-  for (int i = 0; i < iters; ++i) {
-    a0 = fma(a0, m, c); a1 = fma(a1, m, c); a2 = fma(a2, m, c); a3 = fma(a3, m, c);
-    a4 = fma(a4, m, c); a5 = fma(a5, m, c); a6 = fma(a6, m, c); a7 = fma(a7, m, c);
-  }
-  const T r = ((a0 + a1) + (a2 + a3)) + ((a4 + a5) + (a6 + a7));
-  if (r == (T)-12345.678) *sink = (float)r;  // never true; keeps the loop alive
-}
-
-__global__ void probe_rsqrt_kernel(int iters, float* sink) {
-  float a0 = 1.0f + threadIdx.x, a1 = a0 + 1.f, a2 = a0 + 2.f, a3 = a0 + 3.f;
-  float a4 = a0 + 4.f, a5 = a0 + 5.f, a6 = a0 + 6.f, a7 = a0 + 7.f;
-  for (int i = 0; i < iters; ++i) {
-    a0 = rsqrtf(a0); a1 = rsqrtf(a1); a2 = rsqrtf(a2); a3 = rsqrtf(a3);
-    a4 = rsqrtf(a4); a5 = rsqrtf(a5); a6 = rsqrtf(a6); a7 = rsqrtf(a7);
-  }
-  const float r = ((a0 + a1) + (a2 + a3)) + ((a4 + a5) + (a6 + a7));
-  if (r == -12345.678f) *sink = r;
-}
-
-// Issue-mix probes (profiles/probe_mix.py): 8 independent instructions per iteration.
-//   MODE 3: 8 FFMA2        MODE 4: 6 FFMA2 + 2 MUFU.RSQ
-//   MODE 5: 6 FFMA + 2 MUFU.RSQ     MODE 6: 12 FFMA + 2 MUFU.RSQ (the scalar work of mode 4)
-//   MODE 7: mode 4 + 1 broadcast LDS.128 feeding the FFMA2s
-template <int MODE>
-__global__ void probe_mix_kernel(int iters, float* sink) {
-  const float t = 1e-3f * threadIdx.x;
-  f32x2 p[6];
-  float f[12], r0 = 1.5f + t, r1 = 2.5f + t;
-  const f32x2 m2 = pack2(0.999f, 0.998f), c2 = pack2(1e-3f, 2e-3f);
-#pragma unroll
-  for (int k = 0; k < 6; ++k) p[k] = pack2(t + k, t - k);
-#pragma unroll
-  for (int k = 0; k < 12; ++k) f[k] = t + 0.5f * k;
-  f32x2 q0 = pack2(t, 1.f), q1 = pack2(t, 2.f);
-  __shared__ ulonglong2 rowbuf[64];
-  if (MODE == 7) {
-    if (threadIdx.x < 64) rowbuf[threadIdx.x] = make_ulonglong2(m2, c2);
-    __syncthreads();
-  }
-  for (int i = 0; i < iters; ++i) {
-    if (MODE == 3 || MODE == 4) {
-#pragma unroll
-      for (int k = 0; k < 6; ++k) p[k] = fma2(p[k], m2, c2);
-    }
-    if (MODE == 7) {  // mode 4 with its operands broadcast from shared memory (one LDS.128 per round)
-      const ulonglong2 q = rowbuf[i & 63];
-#pragma unroll
-      for (int k = 0; k < 6; ++k) p[k] = fma2(p[k], q.x, q.y);
-    }
-    if (MODE == 3) { q0 = fma2(q0, m2, c2); q1 = fma2(q1, m2, c2); }
-    if (MODE == 5 || MODE == 6) {
-#pragma unroll
-      for (int k = 0; k < (MODE == 5 ? 6 : 12); ++k) f[k] = fmaf(f[k], 0.999f, 1e-3f);
-    }
-    if (MODE != 3) { r0 = rsqrtf(r0); r1 = rsqrtf(r1); }
-  }
-  float lo, hi, r = r0 + r1;
-#pragma unroll
-  for (int k = 0; k < 6; ++k) { unpack2(p[k], lo, hi); r += lo + hi; }
-  unpack2(q0, lo, hi); r += lo + hi;
-  unpack2(q1, lo, hi); r += lo + hi;
-#pragma unroll
-  for (int k = 0; k < 12; ++k) r += f[k];
-  if (r == -12345.678f) *sink = r;
-}
 
 // ------------------------------------------------------------------ numpy SeedSequence
 // Published algorithm (numpy/random/bit_generator.pyx, after M.E. O'Neill's seed_seq_fe):
@@ -278,17 +203,22 @@ int mch_optimize_batch(const mch_optimize_desc* d, void* stream) {
     return fail(MCH_ERR_INVALID, "mch_optimize_batch: null required pointer");
   int smem = mch_optimize_smem_bytes(d->n_atoms, d->n_subunits, d->n_bonds, d->max_subunit_atoms, d->compute_dtype);
   if (smem < 0) return smem;
+  // chains that are (or will be) resident together: a caller that cuts one batch into several
+  // launches (BatchPlan's pipelined slices) says so, and every slice gets the batch's choices
+  const int sms = sm_count();
+  const long long batch = d->resident_chains_hint > d->n_chains ? d->resident_chains_hint : d->n_chains;
   // Thread-block cluster per chain: worth it when the GPU would otherwise be mostly idle and the
   // sweep is long enough to pay for one cluster barrier per step (big molecule, few chains).
   int cluster = d->cluster_size;
   if (cluster != 0 && cluster != 1 && cluster != 2 && cluster != 4 && cluster != 8)
     return fail(MCH_ERR_INVALID, "mch_optimize_batch: cluster_size must be 0 (auto), 1, 2, 4 or 8, got %d", cluster);
+  // an explicit block size outside what a chain on a cluster takes keeps the chain on one CTA
+  const bool threads_fit_cluster = d->threads_per_chain == 0 || (d->threads_per_chain >= 64 && d->threads_per_chain <= 512);
   if (cluster == 0) {
     cluster = 1;
-    if (d->n_atoms >= 768 && d->num_steps > 1) {  // measured: profiles/r01_cluster_chain.txt
-      const int sms = sm_count();
+    if (d->n_atoms >= 768 && d->num_steps > 1 && threads_fit_cluster) {  // measured: profiles/r01_cluster_chain.txt
       for (int g = d->n_atoms >= 2048 ? 8 : 4; g >= 2; g /= 2)
-        if ((long long)d->n_chains * g <= sms) {
+        if (batch * g <= sms) {
           int defer_unused;
           if (plan_chain_smem(d->n_atoms, d->n_subunits, d->n_bonds, d->max_subunit_atoms, d->compute_dtype,
                               &defer_unused, g) <= kMaxSmem) cluster = g;
@@ -304,12 +234,17 @@ int mch_optimize_batch(const mch_optimize_desc* d, void* stream) {
   } else {
     (void)plan_chain_smem(d->n_atoms, d->n_subunits, d->n_bonds, d->max_subunit_atoms, d->compute_dtype, &defer);
   }
+  const int by_smem = kMaxSmem / smem;
+  const long long spread = (batch + sms - 1) / sms;
+  const int per_sm = (int)(spread < by_smem ? spread : by_smem);
+  bool regs64 = false;
   int threads;
   int rc = check_threads(d->threads_per_chain,
-                         cluster > 1 ? 512 : auto_threads(d->n_atoms, d->n_chains, smem, d->compute_dtype),
+                         cluster > 1 ? 512 : auto_threads(d->n_atoms, per_sm, by_smem, d->compute_dtype, &regs64),
                          d->compute_dtype == MCH_F64 ? 512 : 1024, &threads);
   if (rc != MCH_OK) return rc;
-  if (cluster > 1 && (threads < 64 || threads > 512))
+  if (d->threads_per_chain > 0) regs64 = false;  // an explicit block size: the 128-register family up to 512 threads
+  if (cluster > 1 && (threads < 64 || threads > 512))  // only reachable with an explicit cluster_size
     return fail(MCH_ERR_INVALID, "a chain on a cluster takes 64 to 512 threads per CTA, got %d", threads);
 
   mch::OptArgs a;
@@ -327,7 +262,7 @@ int mch_optimize_batch(const mch_optimize_desc* d, void* stream) {
   a.inexact_undo = d->inexact_undo;
   a.defer = defer;
   a.cluster = cluster;
-  a.latency = d->n_chains <= sm_count() ? 1 : 0;
+  a.regs64 = regs64 ? 1 : 0;
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
   const bool io_f64 = d->io_dtype == MCH_F64;
   return d->compute_dtype == MCH_F64 ? mch::launch_optimize_f64(io_f64, mk, a, threads, smem, s)
@@ -363,7 +298,8 @@ int mch_potential_batch(const void* pos, int io_dtype, int compute_dtype, int n_
 
 int mch_collapse_batch(const mch_collapse_desc* d, void* stream) {
   if (!d) return fail(MCH_ERR_INVALID, "mch_collapse_batch: null descriptor");
-  if (d->n_mol <= 0 || d->n_atoms <= 0 || d->n_subunits <= 0 || d->n_bonds < 0 || d->max_steps < 0)
+  if (d->n_mol <= 0 || d->n_atoms <= 0 || d->n_subunits <= 0 || d->n_bonds < 0 || d->max_steps < 0 ||
+      d->n_moving_subunits < 0 || d->n_moving_subunits > d->n_subunits)
     return fail(MCH_ERR_INVALID, "mch_collapse_batch: bad sizes");
   if (!dtype_ok(d->io_dtype) || !dtype_ok(d->compute_dtype)) return fail(MCH_ERR_INVALID, "mch_collapse_batch: unknown dtype");
   if (!d->pos_in || !d->pos_out || !d->perm || !d->su_offsets || !d->n_heavy || (d->n_bonds > 0 && !d->bonds) ||
@@ -383,6 +319,7 @@ int mch_collapse_batch(const mch_collapse_desc* d, void* stream) {
   mch::ColArgs a;
   a.pos_in = d->pos_in; a.pos_in_stride = d->pos_in_mol_stride; a.pos_out = d->pos_out;
   a.C = d->n_mol; a.N = d->n_atoms; a.S = d->n_subunits; a.B = d->n_bonds;
+  a.S_moving = d->n_moving_subunits > 0 ? d->n_moving_subunits : d->n_subunits;
   a.perm = d->perm; a.su_off = d->su_offsets; a.n_heavy = d->n_heavy; a.bonds = d->bonds;
   a.step_size = d->step_size; a.threshold = d->distance_threshold; a.scale_steps = d->scale_steps;
   a.max_steps = d->max_steps;
@@ -434,32 +371,6 @@ int mch_pcg64_stream_check(uint64_t* rng_state, int rounds, uint32_t bound, int6
   }
   mch::pcg_store(g, rng_state);
   return MCH_OK;
-}
-
-int mch_probe_fma(int dtype, int blocks, int threads, int iters, float* sink, void* stream) {
-  if (blocks <= 0 || threads <= 0 || threads > 1024 || iters <= 0 || !sink) return fail(MCH_ERR_INVALID, "mch_probe_fma: bad arguments");
-  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
-  if (dtype == MCH_F64) probe_fma_kernel<double><<<blocks, threads, 0, s>>>(iters, sink);
-  else if (dtype == MCH_F32) probe_fma_kernel<float><<<blocks, threads, 0, s>>>(iters, sink);
-  else if (dtype == 2) probe_rsqrt_kernel<<<blocks, threads, 0, s>>>(iters, sink);
-  else if (dtype == 3) probe_mix_kernel<3><<<blocks, threads, 0, s>>>(iters, sink);
-  else if (dtype == 4) probe_mix_kernel<4><<<blocks, threads, 0, s>>>(iters, sink);
-  else if (dtype == 5) probe_mix_kernel<5><<<blocks, threads, 0, s>>>(iters, sink);
-  else if (dtype == 6) probe_mix_kernel<6><<<blocks, threads, 0, s>>>(iters, sink);
-  else if (dtype == 7) probe_mix_kernel<7><<<blocks, threads, 0, s>>>(iters, sink);
-  else return fail(MCH_ERR_INVALID, "mch_probe_fma: dtype must be 0 (f64 fma), 1 (f32 fma), 2 (f32 rsqrt) or 3..7 (issue mixes)");
-  cudaError_t e = cudaGetLastError();
-  if (e != cudaSuccess) return fail(MCH_ERR_CUDA, "mch_probe_fma: %s", cudaGetErrorString(e));
-  return MCH_OK;
-}
-
-int mch_probe_sweep(int blocks, int threads, int iters, int with_barrier, int n_rows, int n_cols, float* sink, void* stream) {
-  if (blocks <= 0 || threads < 32 || threads > 256 || threads % 32 || iters <= 0 || n_rows < 1 || n_rows > 60 ||
-      n_cols < 1 || n_cols > 950 || !sink)
-    return fail(MCH_ERR_INVALID, "mch_probe_sweep: bad arguments");
-  const int rc = mch::launch_probe_sweep(blocks, threads, iters, with_barrier, n_rows, n_cols, sink,
-                                         reinterpret_cast<cudaStream_t>(stream));
-  return rc == 0 ? MCH_OK : fail(MCH_ERR_CUDA, "mch_probe_sweep: launch failed");
 }
 
 }  // extern "C"

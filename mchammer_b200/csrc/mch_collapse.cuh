@@ -27,6 +27,9 @@ struct ColArgs {
   long long pos_in_stride;  // 0 -> broadcast chain 0
   void* pos_out;            // [C][N][3]
   int C, N, S, B;
+  int S_moving;        // the first S_moving subunits are the caller's; a trailing group of atoms that are in no
+                       // subunit (if any) never moves, is not contact-tested and does not enter the scales
+                       // (reference collapser.py:56-82, :106-157 loop over the caller's dict only)
   const int* perm;     // [N] slot -> atom id
   const int* su_off;   // [S+1]
   const int* n_heavy;  // [S] non-H atoms per subunit (leading slots of the subunit)
@@ -100,7 +103,8 @@ mch_collapse_kernel(const __grid_constant__ ColArgs a) {
     for (int s = 0; s <= S; ++s) loff[s] += h;
   }
   __syncthreads();
-  const int nh = hoff[S];
+  const int Sm = a.S_moving;
+  const int nh = hoff[Sm];  // heavy atoms that take part in the contact test (the caller's subunits only)
   int* inv = reinterpret_cast<int*>(X);  // atom id -> internal slot, N ints: borrows X (positions are loaded later)
   for (int sidx = warp; sidx < S; sidx += nwarps) {
     const int r0 = a.su_off[sidx], n = a.su_off[sidx + 1] - r0, nh_s = a.n_heavy[sidx];
@@ -216,6 +220,7 @@ mch_collapse_kernel(const __grid_constant__ ColArgs a) {
       tx = warp_sum(tx) / N; ty = warp_sum(ty) / N; tz = warp_sum(tz) / N;
       double big = 0.0;
       for (int s = lane; s < S; s += 32) {
+        if (s >= Sm) { vec[3 * s] = 0.0; vec[3 * s + 1] = 0.0; vec[3 * s + 2] = 0.0; continue; }  // static group
         const double n = (double)((hoff[s + 1] - hoff[s]) + (loff[s + 1] - loff[s]));
         const double vx = csum[3 * s] / n - tx, vy = csum[3 * s + 1] / n - ty, vz = csum[3 * s + 2] / n - tz;
         vec[3 * s] = vx; vec[3 * s + 1] = vy; vec[3 * s + 2] = vz;
@@ -223,7 +228,7 @@ mch_collapse_kernel(const __grid_constant__ ColArgs a) {
       }
       big = warp_max(big);
       __syncwarp();
-      for (int s = lane; s < S; s += 32) {
+      for (int s = lane; s < Sm; s += 32) {
         const double vx = vec[3 * s], vy = vec[3 * s + 1], vz = vec[3 * s + 2];
         const double sc = a.scale_steps ? sqrt(vx * vx + vy * vy + vz * vz) / big : 1.0;
         vec[3 * s] = (step * vx) * sc; vec[3 * s + 1] = (step * vy) * sc; vec[3 * s + 2] = (step * vz) * sc;
@@ -232,6 +237,7 @@ mch_collapse_kernel(const __grid_constant__ ColArgs a) {
     __syncthreads();
     for (int n = tid; n < N; n += nt) {
       const int s = suof[n];
+      if (s >= Sm) continue;  // atoms in no subunit keep their positions bit for bit
       X[n] = (T)((double)X[n] - vec[3 * s]);
       Y[n] = (T)((double)Y[n] - vec[3 * s + 1]);
       Z[n] = (T)((double)Z[n] - vec[3 * s + 2]);

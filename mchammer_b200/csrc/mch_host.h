@@ -48,8 +48,6 @@ int launch_clustered(K kernel, const A& args, int blocks, int threads, int smem,
 int launch_optimize_f32(bool io_f64, int mu_kind, const OptArgs& a, int threads, int smem, cudaStream_t s);
 int launch_optimize_f64(bool io_f64, int mu_kind, const OptArgs& a, int threads, int smem, cudaStream_t s);
 
-int launch_probe_sweep(int blocks, int threads, int iters, int with_barrier, int nrows, int ncols, float* sink, cudaStream_t s);
-
 template <typename T, typename Tio, int NTMAX>
 int launch_optimize_nt(int mk, const OptArgs& a, int threads, int smem, cudaStream_t s) {
   switch (mk) {
@@ -74,14 +72,16 @@ int launch_optimize_cluster(int mk, const OptArgs& a, int threads, int smem, cud
 template <typename T, typename Tio>
 int launch_optimize_io(int mk, const OptArgs& a, int threads, int smem, cudaStream_t s) {
   if (a.cluster > 1) return launch_optimize_cluster<T, Tio>(mk, a, threads, smem, s);
-  // a lone fp32 chain of 129..512 threads: the same instantiation as a cluster of one (128 registers;
-  // the throughput-oriented large block is held to 64 and spills in the control section)
-  if (sizeof(T) == 4 && a.latency && threads > 128 && threads <= 512)
-    return launch_optimize_cluster<T, Tio>(mk, a, threads, smem, s);
-  if (sizeof(T) == 4 && threads <= 32) return launch_optimize_nt<T, Tio, 32>(mk, a, threads, smem, s);
-  if (sizeof(T) == 4 && threads <= 64) return launch_optimize_nt<T, Tio, 64>(mk, a, threads, smem, s);
-  return threads <= small_block<T>() ? launch_optimize_nt<T, Tio, small_block<T>()>(mk, a, threads, smem, s)
-                                     : launch_optimize_nt<T, Tio, large_block<T>()>(mk, a, threads, smem, s);
+  // blocks that share an SM with so many others that 128 registers per thread do not fit
+  // (a.regs64, set by the host), and blocks of more than 512 threads: the 64-register instantiation
+  if constexpr (sizeof(T) == 4) {
+    if (a.regs64 || threads > 512) return launch_optimize_nt<T, Tio, 1024>(mk, a, threads, smem, s);
+    if (threads <= 32) return launch_optimize_nt<T, Tio, 32>(mk, a, threads, smem, s);
+    if (threads <= 64) return launch_optimize_nt<T, Tio, 64>(mk, a, threads, smem, s);
+  }
+  if (threads <= 128) return launch_optimize_nt<T, Tio, 128>(mk, a, threads, smem, s);
+  if (threads <= 256) return launch_optimize_nt<T, Tio, 256>(mk, a, threads, smem, s);
+  return launch_optimize_cluster<T, Tio>(mk, a, threads, smem, s);  // 257..512 threads: a cluster of one
 }
 
 }  // namespace mch

@@ -69,7 +69,7 @@ struct OptArgs {
   int inexact_undo;          // 1: reproduce (p - v) + v on reject (fp64 parity)
   int defer;                 // 1: deferred control work + second column-sum buffer (see header)
   int cluster;               // CTAs per chain (thread-block cluster; 1 = the chain is one CTA)
-  int latency;               // 1: at most one chain per SM (host hint: prefer the 128-register instantiations)
+  int regs64;                // 1: the host wants the 64-register (1024-thread) fp32 instantiation: two 512-thread chains per SM
 };
 
 struct Ctl {
@@ -140,23 +140,16 @@ template <typename Tio> MCH_D void store_io(void* base, long long idx, double v)
 // refreshed; larger ones by the whole warp.
 constexpr int REGROUP_SMALL = 64;
 
-#ifndef MCH_F32_THREADS_PER_SM
-#define MCH_F32_THREADS_PER_SM 768  // 128-thread fp32 blocks: 80 registers per thread, 6 chains per SM
-#endif
-
-// NTMAX: largest block an instantiation may be launched with; together with the minimum
-// number of resident blocks it fixes the register budget.  Chains that share an SM:
-//   32 threads (10 chains/SM), 64 threads (8 chains/SM, 128 registers -- the S1 default),
-//   128 threads (fp32: MCH_F32_THREADS_PER_SM / 128 = 6 chains, 80 registers; fp64: 4 chains,
-//   128 registers).  A molecule whose shared memory leaves room for one chain per SM uses the
-//   large-block instantiation (fp32: up to 1024 threads at 64 registers; fp64: up to 512 at 128)
-//   so that the single chain can still fill the SM's warp slots.
-template <typename T> constexpr int small_block() { return 128; }
+// NTMAX: largest block an instantiation may be launched with; together with the minimum number
+// of resident blocks it fixes the register budget.  Every instantiation but the 1024-thread one
+// gets 128 registers per thread (no spills in the control section, rows fetched a whole trip
+// ahead in the packed tile):
+//   32 threads (10 chains/SM), 64 (8 chains/SM -- the S1 default), 128 (4), 256 (2), 512 (1; also the
+//   cluster-capable instantiation).  1024 threads at 64 registers (fp32 only) serves molecules of
+//   which two 512-thread chains share an SM (M12L24) and chains that want more than 512 threads.
 template <typename T> constexpr int large_block() { return sizeof(T) == 4 ? 1024 : 512; }
 template <typename T, int NTMAX> constexpr int min_blocks_per_sm() {
-  return NTMAX == 32 ? 10  // one-warp chains
-         : NTMAX == 64 ? 8   // two-warp chains: shared memory allows 8 per SM, so 128 registers each
-         : NTMAX == small_block<T>() ? (sizeof(T) == 4 ? MCH_F32_THREADS_PER_SM : 512) / NTMAX : 1;
+  return NTMAX == 32 ? 10 : NTMAX == 64 ? 8 : NTMAX == 128 ? 4 : NTMAX == 256 ? 2 : 1;
 }
 
 // CL: the instantiation can run a chain on a thread-block cluster of a.cluster CTAs (launched with
@@ -246,7 +239,7 @@ mch_optimize_kernel(const __grid_constant__ OptArgs a) {
   constexpr bool kFast = sizeof(T) == 4;  // fp32 mode: cheaper centroid bookkeeping
   constexpr bool kXF = kFast && (MCH_XF != 0);  // expanded-form squared distances (mch_device.cuh)
   constexpr bool kX2 = kXF && (MCH_F32X2 != 0);  // packed-instruction tile
-  constexpr int kRot3 = !(kX2 && (MCH_X2_ROT3 != 0)) ? 0 : (NTMAX <= 64 ? 2 : 1);  // 2: deep row prefetch (128 registers)
+  constexpr int kRot3 = !(kX2 && (MCH_X2_ROT3 != 0)) ? 0 : (NTMAX <= 512 ? 2 : 1);  // 2: deep row prefetch (128 registers)
   const bool kDefer = a.defer != 0;  // host policy: off when the second buffer would cost a resident chain
   // re-sum an accepted move's row of E with all warps (coop_row) where warp 0 alone would take long
   const bool kCoop = nwarps > 1 && ((CL && G > 1) || !kDefer || a.max_su > REGROUP_SMALL);

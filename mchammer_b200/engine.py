@@ -100,6 +100,7 @@ def optimize_on_device(
     threads_per_chain: int = 0,
     out: OptimizeOutput | None = None,
     cluster_size: int = 0,
+    resident_chains_hint: int = 0,
 ) -> OptimizeOutput:
     """Launch the resident Metropolis kernel for ``n_chains`` chains (asynchronous)."""
     torch = native.require_cuda()
@@ -151,7 +152,7 @@ def optimize_on_device(
         desc.io_dtype, desc.compute_dtype = io_code, compute_code
         desc.inexact_undo = 1 if inexact_undo else 0
         desc.threads_per_chain = int(threads_per_chain)
-        desc.cluster_size, desc.reserved = int(cluster_size), 0
+        desc.cluster_size, desc.resident_chains_hint = int(cluster_size), int(resident_chains_hint)
         desc.pos_in = ptr(pos_in)
         desc.pos_in_chain_stride = 0 if pos_in.shape[0] == 1 and n_chains > 1 else n * 3
         desc.pos_out = ptr(out.positions)
@@ -242,6 +243,8 @@ def collapse_on_device(
         d.io_dtype, d.compute_dtype = _dtype_code(torch, pos_in.dtype), _precision_code(precision)
         d.scale_steps, d.max_steps = int(bool(scale_steps)), int(max_steps)
         d.trace_capacity, d.threads_per_mol = int(trace_capacity), int(threads_per_mol)
+        # atoms outside every subunit form a trailing static group that the Collapser must leave alone
+        d.n_moving_subunits, d.reserved = topo.n_user_subunits, 0
         d.step_size, d.distance_threshold = float(step_size), float(distance_threshold)
         d.pos_in = ptr(pos_in)
         d.pos_in_mol_stride = 0 if pos_in.shape[0] == 1 and n_mol > 1 else n * 3

@@ -20,8 +20,7 @@ MCH_F64, MCH_F32 = 0, 1
 
 EXPORTS = (
     "mch_optimize_batch", "mch_optimize_smem_bytes", "mch_potential_batch",
-    "mch_collapse_batch", "mch_pcg64_seed", "mch_pcg64_stream_check", "mch_probe_fma",
-    "mch_probe_sweep",
+    "mch_collapse_batch", "mch_pcg64_seed", "mch_pcg64_stream_check",
     "mch_last_error", "mch_version",
 )
 
@@ -43,7 +42,7 @@ class OptimizeDesc(C.Structure):
         ("n_chains", C.c_int32), ("n_atoms", C.c_int32), ("n_subunits", C.c_int32),
         ("n_bonds", C.c_int32), ("max_subunit_atoms", C.c_int32), ("num_steps", C.c_int32),
         ("io_dtype", C.c_int32), ("compute_dtype", C.c_int32), ("inexact_undo", C.c_int32),
-        ("threads_per_chain", C.c_int32), ("cluster_size", C.c_int32), ("reserved", C.c_int32),
+        ("threads_per_chain", C.c_int32), ("cluster_size", C.c_int32), ("resident_chains_hint", C.c_int32),
         ("pos_in", C.c_void_p), ("pos_in_chain_stride", C.c_int64), ("pos_out", C.c_void_p),
         ("perm", C.c_void_p), ("su_offsets", C.c_void_p), ("bonds", C.c_void_p),
         ("bond_su", C.c_void_p),
@@ -62,7 +61,7 @@ class CollapseDesc(C.Structure):
         ("n_mol", C.c_int32), ("n_atoms", C.c_int32), ("n_subunits", C.c_int32),
         ("n_bonds", C.c_int32), ("io_dtype", C.c_int32), ("compute_dtype", C.c_int32),
         ("scale_steps", C.c_int32), ("max_steps", C.c_int32), ("trace_capacity", C.c_int32),
-        ("threads_per_mol", C.c_int32),
+        ("threads_per_mol", C.c_int32), ("n_moving_subunits", C.c_int32), ("reserved", C.c_int32),
         ("step_size", C.c_double), ("distance_threshold", C.c_double),
         ("pos_in", C.c_void_p), ("pos_in_mol_stride", C.c_int64), ("pos_out", C.c_void_p),
         ("perm", C.c_void_p), ("su_offsets", C.c_void_p), ("n_heavy", C.c_void_p),
@@ -105,10 +104,6 @@ def lib() -> C.CDLL:
     handle.mch_pcg64_seed.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
     handle.mch_pcg64_stream_check.restype = C.c_int
     handle.mch_pcg64_stream_check.argtypes = [C.c_void_p, C.c_int, C.c_uint32, C.c_void_p, C.c_void_p]
-    handle.mch_probe_fma.restype = C.c_int
-    handle.mch_probe_fma.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
-    handle.mch_probe_sweep.restype = C.c_int
-    handle.mch_probe_sweep.argtypes = [C.c_int] * 6 + [C.c_void_p, C.c_void_p]
     return handle
 
 

@@ -90,7 +90,12 @@ class Optimizer:
         torch = native.require_cuda()
         dev = self._torch_device()
         pos = torch.from_numpy(np.ascontiguousarray(position_matrix, dtype=np.float64)).to(dev)
-        bonds = np.array([(int(b[0]), int(b[1])) for b in bond_pair_ids], dtype=np.int32).reshape(-1)
+        bonds = np.array([(int(b[0]), int(b[1])) for b in bond_pair_ids], dtype=np.int64).reshape(-1)
+        n_atoms = int(np.shape(position_matrix)[0])
+        if bonds.size and (bonds.min() < -n_atoms or bonds.max() >= n_atoms):
+            # the reference indexes the position matrix with these ids (utilities.py:13-21): IndexError
+            raise IndexError("bond_pair_ids refers to an atom id outside the molecule")
+        bonds = np.where(bonds < 0, bonds + n_atoms, bonds).astype(np.int32)  # numpy-style negative ids
         bonds_dev = torch.from_numpy(bonds).to(dev) if bonds.size else None
         u, unb, far = engine.potential_on_device(
             pos, bonds_dev, bonds.size // 2, self._params(), self._precision

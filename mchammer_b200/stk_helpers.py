@@ -54,3 +54,64 @@ def molecule_from_stk(state) -> Molecule:
             for i, b in enumerate(state.get_bonds())
         )
     return Molecule(atoms=atoms, bonds=bonds, position_matrix=state.get_position_matrix())
+
+
+def optimize_batch(states, optimizer, seeds=1000, devices=None):
+    """Optimise many stk-shaped molecules/states in batched launches (NEW; no reference counterpart).
+
+    Per state this is the wiring of reference tests/stk_reproduction/test_stk.py:97-135 (what
+    stk's ``MCHammer`` optimizer does): atoms + sorted bonds -> :class:`Molecule`,
+    ``bond_pair_ids = get_long_bond_ids(state)``, ``subunits = get_subunits(state)``, then
+    ``Optimizer(..., random_seed=seed).get_result(...)``.  States that share a topology (same
+    atom count, long bonds and building-block assignment -- e.g. conformers or a screening library
+    built from one topology graph) go to the device as ONE ``get_results_batch`` call with
+    per-chain start geometries; different topologies are grouped and run one group after another.
+
+    optimizer: a :class:`mchammer_b200.Optimizer` (its potential parameters, num_steps and
+        precision are used; its own generator is not touched).
+    seeds: one integer for every state (stk constructs a fresh ``Optimizer(random_seed=1000)``
+        per molecule) or one integer per state.
+
+    Returns a list, in input order, of ``(new_state, record)``: ``new_state`` is
+    ``state.with_position_matrix(final)`` when the state has that method (stk molecules do), else
+    a :class:`Molecule`; ``record`` is a dict with the last step's ``system_potential``,
+    ``nonbonded_potential``, ``max_bond_distance``, ``passed`` and ``n_accepted``.
+    """
+    import numpy as np
+
+    states = list(states)
+    if isinstance(seeds, (int, np.integer)):
+        seeds = [int(seeds)] * len(states)
+    seeds = [int(s) for s in seeds]
+    if len(seeds) != len(states):
+        raise ValueError("seeds must be one integer or one integer per state")
+    groups: dict = {}
+    lowered = []
+    for index, state in enumerate(states):
+        long_bonds = get_long_bond_ids(state)
+        subunits = {k: list(v) for k, v in get_subunits(state).items()}
+        positions = np.asarray(state.get_position_matrix(), dtype=np.float64)
+        key = (positions.shape[0], long_bonds, tuple((k, tuple(v)) for k, v in subunits.items()))
+        groups.setdefault(key, []).append(index)
+        lowered.append((long_bonds, subunits, positions))
+    out: list = [None] * len(states)
+    for members in groups.values():
+        first = members[0]
+        long_bonds, subunits, _ = lowered[first]
+        template = molecule_from_stk(states[first])
+        stack = np.stack([lowered[i][2] for i in members])
+        res = optimizer.get_results_batch(template, long_bonds, subunits, seeds=[seeds[i] for i in members],
+                                          positions=stack, devices=devices)
+        for slot, index in enumerate(members):
+            final = np.array(res.positions[slot], dtype=np.float64)
+            state = states[index]
+            new_state = (state.with_position_matrix(final) if hasattr(state, "with_position_matrix")
+                         else molecule_from_stk(state).with_position_matrix(final))
+            out[index] = (new_state, {
+                "system_potential": float(res.system_potential[slot]),
+                "nonbonded_potential": float(res.nonbonded_potential[slot]),
+                "max_bond_distance": float(res.max_bond_distance[slot]),
+                "passed": None if res.last_passed[slot] < 0 else bool(res.last_passed[slot]),
+                "n_accepted": int(res.n_accepted[slot]),
+            })
+    return out

@@ -28,18 +28,8 @@ pos = torch.from_numpy(np.stack([base * (1.0 + 0.004 * rng.random()) for _ in ra
 
 
 def pipe_peak(code):
-    lib = native.lib()
-    sink = torch.zeros(1, dtype=torch.float32, device=dev)
-    blocks, threads, iters = 148 * 8, 256, 1 << 14
-    best = 0.0
-    for _ in range(3):
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        native.check(lib.mch_probe_fma(code, blocks, threads, iters, C.c_void_p(sink.data_ptr()),
-                                       C.c_void_p(torch.cuda.current_stream().cuda_stream)), "probe")
-        e1.record(); e1.synchronize()
-        best = max(best, (4.0 if code == 3 else 2.0) * 8 * iters * blocks * threads / (e0.elapsed_time(e1) * 1e-3))
-    return best
+    from profiles import probes
+    return probes.pipe_peak(torch, code, dev) * 1e12
 
 
 for precision in ("fp64", "fp32"):

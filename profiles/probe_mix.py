@@ -2,17 +2,14 @@
 
 Prints warp instructions per clock per SM sub-partition (one scheduler issues at most 1.0).
 """
-import ctypes as C
 import sys
 
 import torch
 
 sys.path.insert(0, ".")
-from mchammer_b200 import native
+from profiles import probes
 
-lib = native.lib()
 sink = torch.zeros(1, dtype=torch.float32, device="cuda")
-stream = torch.cuda.current_stream().cuda_stream
 props = torch.cuda.get_device_properties(0)
 sms, clk = props.multi_processor_count, 1.965e9
 modes = {1: ("8 FFMA", 8), 2: ("8 MUFU.RSQ", 8), 3: ("8 FFMA2", 8), 4: ("6 FFMA2 + 2 MUFU.RSQ", 8),
@@ -23,12 +20,7 @@ for threads, per_sm in ((256, 8), (128, 8), (64, 8)):
         blocks, iters = sms * per_sm, 1 << 14
         best = 1e30
         for _ in range(3):
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record()
-            native.check(lib.mch_probe_fma(mode, blocks, threads, iters, C.c_void_p(sink.data_ptr()),
-                                           C.c_void_p(stream)), "probe")
-            e1.record(); e1.synchronize()
-            best = min(best, e0.elapsed_time(e1) * 1e-3)
+            best = min(best, probes.probe_fma(torch, mode, blocks, threads, iters, sink) * 1e-3)
         warp_instr = n_instr * iters * blocks * threads / 32
         cycles_per_round = best * clk * sms * 4 / (iters * blocks * threads / 32)
         print(f"{threads:4d} thr x {per_sm}/SM  {name:26s} {warp_instr / best / clk / sms / 4:.3f} warp-instr/clk/SMSP"

@@ -267,5 +267,37 @@ def main():
     print("done")
 
 
+def main_round2():
+    """Cases added in round 2 (`python tests/golden/make_golden.py r2` writes only these)."""
+    # ---------------- overlapping subunits, the reference's semantics (optimizer.py:220-226, :248-252):
+    # a bond end belongs to the FIRST dict entry that lists it; a move translates EVERY atom the chosen
+    # entry lists (shared atoms included); the subunit centroid is the mean over the listed ids
+    el, pos, bonds, _ = load("benzene.mol")
+    lb = ((2, 3), (1, 5))
+    su = {0: [0, 1, 2, 7, 8, 9, 3], 1: [3, 4, 5, 6, 10, 11]}          # atom 3 (a bond end) in both
+    run_optimizer_case("benzene_overlap_seed9", el, pos, bonds, lb, su, 9, 100, 0.25, 1.2, True)
+    su = {0: [0, 1, 2, 7, 8, 9, 9], 1: [3, 4, 5, 6, 10, 11, 4]}       # an id listed twice in one entry
+    run_optimizer_case("benzene_dup_seed4", el, pos, bonds, lb, su, 4, 100, 0.25, 1.2, True)
+    el, pos, bonds, _ = load("poc.mol")
+    su_bb, start = {}, 0
+    for k, size in enumerate(POC_BB_SIZES):
+        su_bb[k] = list(range(start, start + size))
+        start += size
+    su = {k: list(v) for k, v in su_bb.items()}
+    su[0] = su[0] + [32, 33]        # two atoms of entry 4 also move with entry 0
+    su[6] = [8] + su[6]             # atom 8 (a bond end owned by entry 1) also moves with entry 6
+    su[4] = su[4][:-1]              # atom 39 is in no entry: static, still interacts
+    run_optimizer_case("poc_overlap_seed3", el, pos, bonds, POC_LONG_BONDS, su, 3, 300, 0.25, 1.2, False)
+    # ---------------- Collapser with atoms outside every subunit (they never move, are not
+    # contact-tested and do not enter the scales; collapser.py:56-104)
+    su = {k: list(v) for k, v in su_bb.items() if k != 5}
+    run_collapser_case("collapser_poc_loose", el, pos, bonds, POC_LONG_BONDS, su, 0.05, 1.2, True)
+    print("round 2 done")
+
+
 if __name__ == "__main__":
-    main()
+    if "r2" in sys.argv[1:]:
+        main_round2()
+    else:
+        main()
+        main_round2()

@@ -191,11 +191,27 @@ def test_library_exports_every_declared_symbol():
         assert re.search(rf"\bT {name}\b", out), name
 
 
-def test_ctypes_structs_match_header_layout():
-    # sizes follow from the field lists in include/mchammer_b200.h (natural alignment)
-    assert CT.sizeof(native.MchParams) == 7 * 8
-    assert CT.sizeof(native.OptimizeDesc) == 12 * 4 + 8 * 3 + 4 * 8 + 56 + 8 + 5 * 8 + 4 * 8
-    assert CT.sizeof(native.CollapseDesc) == 10 * 4 + 2 * 8 + 3 * 8 + 4 * 8 + 4 * 8 + 2 * 8
+def test_ctypes_structs_match_header_layout(tmp_path):
+    # the C compiler's view of include/mchammer_b200.h against the ctypes mirrors: size of every
+    # struct and offset of every field
+    structs = {"mch_params": native.MchParams, "mch_optimize_desc": native.OptimizeDesc,
+               "mch_collapse_desc": native.CollapseDesc}
+    lines = []
+    for cname, ctype in structs.items():
+        lines.append(f'printf("{cname} %zu\\n", sizeof({cname}));')
+        for field, _ in ctype._fields_:
+            lines.append(f'printf("{cname}.{field} %zu\\n", offsetof({cname}, {field}));')
+    src = tmp_path / "layout.c"
+    src.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "mchammer_b200.h"\nint main(void) {\n'
+                   + "\n".join(lines) + "\nreturn 0; }\n")
+    exe = tmp_path / "layout"
+    subprocess.run(["gcc", "-I", os.path.join(REPO, "include"), "-o", str(exe), str(src)], check=True)
+    seen = dict(line.split() for line in subprocess.run([str(exe)], capture_output=True, text=True,
+                                                        check=True).stdout.splitlines())
+    for cname, ctype in structs.items():
+        assert int(seen[cname]) == CT.sizeof(ctype), cname
+        for field, _ in ctype._fields_:
+            assert int(seen[f"{cname}.{field}"]) == getattr(ctype, field).offset, (cname, field)
 
 
 def test_c_seeding_matches_numpy():

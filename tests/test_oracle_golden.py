@@ -17,6 +17,8 @@ OPT_CASES = [
     "benzene_seed1000", "benzene_seed7", "benzene_mu2p5", "benzene_mu6",
     "poc_graph_seed1000", "poc_graph_seed7", "poc_graph_seed42", "poc_bb_seed1000",
     "toy_seed1000",
+    # round 2: overlapping subunits / an id listed twice / an atom in no subunit (reference semantics)
+    "benzene_overlap_seed9", "benzene_dup_seed4", "poc_overlap_seed3",
 ]
 
 
@@ -102,7 +104,7 @@ def test_final_positions_against_committed_example_molfiles():
         assert np.abs(g["final_positions"] - ex[name]).max() < 1.5e-4
 
 
-@pytest.mark.parametrize("case", ["collapser_poc", "collapser_poc_noscale", "collapser_toy"])
+@pytest.mark.parametrize("case", ["collapser_poc", "collapser_poc_noscale", "collapser_toy", "collapser_poc_loose"])
 def test_collapser_bit_exact(case):
     g = load_golden(case)
     is_h = [e == "H" for e in g["elements"]]
