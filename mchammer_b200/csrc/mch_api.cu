@@ -69,27 +69,29 @@ int sm_count() {  // SMs of the current device (queried once per device)
   return cache[dev];
 }
 
-// Block size when the caller leaves it open (measured: DESIGN.md section 8, profiles/r02_chain_sweep*.txt).
+// Block size when the caller leaves it open (measured: profiles/r02_chain_sweep.txt).
 //   per_sm  = chains that will share an SM = min(chains that fit its shared memory, ceil(batch / SMs))
 //   by_smem = chains that fit an SM's shared memory
 // A batch that fills the GPU runs best with few warps per chain and as many resident chains as
 // shared memory allows: every warp of a chain but one idles while the chain's serial control
 // section runs, and with two warps per chain that loss (almost) disappears while eight resident
 // chains keep the pipes busy.  A batch that leaves room (fewer chains per SM than would fit) is
-// bound by the latency of a chain instead, so every chain gets the share of the SM's register
-// file its neighbours leave it -- 512 / per_sm threads at 128 registers -- up to the point where
-// more warps have no column units left to work on.  Molecules of which only two chains fit an SM
-// (M12L24) fill the register file in fp32 with 2 x 512 threads at 64 registers (*regs64).
+// bound by the latency of a chain instead, so a chain gets more warps the fewer neighbours it
+// has -- always at 128 registers per thread -- up to the point where more warps have no column
+// units left to work on (S1 on one GPU, chain-steps/s relative to the full batch: 1024 chains
+// 0.83 -> 0.89 with 128 threads, 512 chains 0.71 -> 0.77, 256 chains 0.47 -> 0.64 with 256).
+// Molecules of which only two chains fit an SM (M12L24) fill the register file in fp32 with
+// 2 x 512 threads at 64 registers (*regs64).
 int auto_threads(int n_atoms, int per_sm, int by_smem, int compute_dtype, bool* regs64) {
   *regs64 = false;
   const bool f64 = compute_dtype == MCH_F64;
   if (n_atoms <= 128) return (per_sm <= 1 && f64) ? 128 : 32;
-  int useful = ((n_atoms / 2 + 31) / 32) * 32;  // about one 64-column unit per warp
-  useful = useful < 128 ? 128 : (useful > 512 ? 512 : useful);
   if (!f64 && by_smem == 2 && per_sm == 2) { *regs64 = true; return 512; }
-  int t = (512 / per_sm) / 32 * 32;
-  const int floor_t = f64 ? 128 : 64;
-  t = t < floor_t ? floor_t : t;
+  // the widest block whose warps all get column units (a warp takes 128 columns per tile call)
+  int useful = ((n_atoms / (f64 ? 2 : 4) + 31) / 32) * 32;
+  useful = useful < 128 ? 128 : (useful > 512 ? 512 : useful);
+  int t = per_sm >= 8 ? 64 : (per_sm >= 3 ? 128 : (per_sm == 2 ? 256 : 512));
+  if (f64 && t < 128) t = 128;
   return t < useful ? t : useful;
 }
 

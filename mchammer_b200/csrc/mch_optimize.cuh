@@ -237,8 +237,12 @@ mch_optimize_kernel(const __grid_constant__ OptArgs a) {
   // ---------------------------------------------------------------- control-warp state
   // (uniform across the 32 lanes of warp 0; other warps never read it)
   constexpr bool kFast = sizeof(T) == 4;  // fp32 mode: cheaper centroid bookkeeping
-  constexpr bool kXF = kFast && (MCH_XF != 0);  // expanded-form squared distances (mch_device.cuh)
-  constexpr bool kX2 = kXF && (MCH_F32X2 != 0);  // packed-instruction tile
+  // expanded-form squared distances (mch_device.cuh): 4 instead of 6 FP instructions per pair.  Relative
+  // rounding noise in r^2 ~ eps (|p_i'| + |p_j'|)^2 / r^2 with coordinates taken from the moving subunit's
+  // centroid: ~1e-6 in fp32 (inside the 1e-4 tolerance), ~1e-14 in fp64 (the parity tolerance is 1e-9;
+  // MCH_XF64 = 0 restores the plain form there)
+  constexpr bool kXF = kFast ? (MCH_XF != 0) : (MCH_XF64 != 0);
+  constexpr bool kX2 = kFast && kXF && (MCH_F32X2 != 0);  // packed-instruction tile
   constexpr int kRot3 = !(kX2 && (MCH_X2_ROT3 != 0)) ? 0 : (NTMAX <= 512 ? 2 : 1);  // 2: deep row prefetch (128 registers)
   const bool kDefer = a.defer != 0;  // host policy: off when the second buffer would cost a resident chain
   // re-sum an accepted move's row of E with all warps (coop_row) where warp 0 alone would take long
