@@ -21,7 +21,7 @@ extern "C" {
 
 #define MCH_OK 0
 #define MCH_ERR_INVALID (-1)   /* bad argument (null pointer, size <= 0, unknown dtype ...) */
-#define MCH_ERR_TOO_LARGE (-2) /* molecule does not fit the 227 KB shared memory of one SM */
+#define MCH_ERR_TOO_LARGE (-2) /* molecule does not fit shared memory (one SM, or a cluster of 16 with row lists) */
 #define MCH_ERR_CUDA (-3)      /* CUDA runtime error; text in mch_last_error()             */
 
 #define MCH_F64 0
@@ -86,6 +86,23 @@ typedef struct mch_optimize_desc {
   int32_t* trace_info;        /* [dev] [n_chains][num_steps] or NULL                      */
   void* trajectory;           /* [dev] [n_chains][num_steps][n_atoms][3] io_dtype or NULL */
   uint64_t* pair_evals;       /* [dev] [n_chains] or NULL: pair terms evaluated           */
+  /* Explicit moving sets (optional; mchammer_b200.lowering builds them).  They are REQUIRED when
+   * the caller's subunits overlap (`general` = 1: a move translates every atom the chosen subunit
+   * LISTS, shared atoms included -- reference optimizer.py:248-252 -- while su_offsets/bond_su
+   * keep the first-owner partition of :220-221), and they let molecules that do not fit one
+   * SM's shared memory (or whose subunit count outgrows the S x S energy table) run with their
+   * state split over a thread-block cluster instead of being refused with MCH_ERR_TOO_LARGE.
+   * `general` = 2 forces that split-state kernel for any input (tests, measurements). */
+  int32_t general;
+  int32_t n_row_lists;        /* the caller's subunits (n_subunits minus the static group); 0 = lists absent */
+  int32_t max_rows;           /* longest row list                                          */
+  int32_t reserved;           /* 0                                                         */
+  const int32_t* bond_slots;  /* [dev] [n_bonds][2] slot of each bond end                  */
+  const int32_t* row_offsets; /* [dev] [n_row_lists + 1]                                   */
+  const int32_t* row_slots;   /* [dev] slots of the atoms each subunit lists, ascending, each once */
+  const int32_t* row_weights; /* [dev] how often the caller's list names that atom (centroid weights) */
+  const int32_t* run_offsets; /* [dev] [n_row_lists + 1]                                   */
+  const int32_t* runs;        /* [dev] [..][2] maximal contiguous slot ranges of each row list */
 } mch_optimize_desc;
 
 int mch_optimize_batch(const mch_optimize_desc* desc, void* stream);

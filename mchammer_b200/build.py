@@ -21,9 +21,9 @@ LIB = os.path.join(PKG, "libmchammer_b200.so")
 PROBES_DIR = os.path.join(os.path.dirname(PKG), "profiles", "probes")
 PROBES_SRC = os.path.join(PROBES_DIR, "mch_probes.cu")
 PROBES_LIB = os.path.join(PROBES_DIR, "libmch_probes.so")
-SOURCES = ["mch_api.cu", "mch_optimize_f32.cu", "mch_optimize_f64.cu"]
+SOURCES = ["mch_api.cu", "mch_optimize_f32.cu", "mch_optimize_f64.cu", "mch_wide_f32.cu", "mch_wide_f64.cu"]
 HEADERS = [
-    "mch_device.cuh", "mch_optimize.cuh", "mch_potential.cuh", "mch_collapse.cuh", "mch_host.h",
+    "mch_device.cuh", "mch_optimize.cuh", "mch_wide.cuh", "mch_potential.cuh", "mch_collapse.cuh", "mch_host.h",
     os.path.join("..", "..", "include", "mchammer_b200.h"),
 ]
 

@@ -13,6 +13,7 @@
 #include "mch_host.h"
 #include "mch_optimize.cuh"
 #include "mch_potential.cuh"
+#include "mch_wide.cuh"
 
 namespace {
 thread_local char g_error[512] = "";
@@ -192,6 +193,61 @@ int mch_optimize_smem_bytes(int n_atoms, int n_subunits, int n_bonds, int max_su
   return total;
 }
 
+namespace {
+// The split-state kernel (csrc/mch_wide.cuh): explicit row lists, state split over a cluster.
+int optimize_wide(const mch_optimize_desc* d, void* stream) {
+  if (d->n_row_lists <= 0 || !d->bond_slots || !d->row_offsets || !d->row_slots || !d->row_weights ||
+      !d->run_offsets || !d->runs || d->max_rows <= 0)
+    return fail(MCH_ERR_INVALID, "mch_optimize_batch: this input needs the explicit row lists (bond_slots, row_*, run_*)");
+  const int tsize = d->compute_dtype == MCH_F64 ? 8 : 4;
+  int G = 0, chunk = 0, smem = 0;
+  for (int g = 1; g <= mch::kWideMaxCluster; g *= 2) {
+    const int ch = mch::align_up((d->n_atoms + g - 1) / g, 64);
+    const long long est = 3LL * ch * tsize;
+    if (est > kMaxSmem) continue;
+    const int total = mch::wide_layout(ch, d->n_bonds, d->max_rows, tsize).total;
+    if (total <= kMaxSmem) { G = g; chunk = ch; smem = total; break; }
+  }
+  if (G == 0) return fail(MCH_ERR_TOO_LARGE, "molecule of %d atoms does not fit the shared memory of a cluster of %d SMs", d->n_atoms, mch::kWideMaxCluster);
+  if (d->cluster_size > 0) {
+    if (d->cluster_size != 1 && d->cluster_size != 2 && d->cluster_size != 4 && d->cluster_size != 8 && d->cluster_size != 16)
+      return fail(MCH_ERR_INVALID, "mch_optimize_batch: cluster_size must be 1, 2, 4, 8 or 16 for the split-state kernel");
+    if (d->cluster_size < G) return fail(MCH_ERR_TOO_LARGE, "the molecule needs a cluster of at least %d CTAs", G);
+    G = d->cluster_size;
+  } else {
+    // few chains of a big molecule: more CTAs per chain while SMs are free and every CTA keeps >= 512 columns
+    const long long batch = d->resident_chains_hint > d->n_chains ? d->resident_chains_hint : d->n_chains;
+    while (G < 8 && batch * 2 * G <= sm_count() && d->n_atoms / (2 * G) >= 512) G *= 2;
+  }
+  chunk = mch::align_up((d->n_atoms + G - 1) / G, 64);
+  smem = mch::wide_layout(chunk, d->n_bonds, d->max_rows, tsize).total;
+  int threads;
+  const int auto_t = chunk <= 64 ? 32 : (chunk <= 256 ? 64 : (chunk <= 1024 ? 128 : (chunk <= 4096 ? 256 : 512)));
+  int rc = check_threads(d->threads_per_chain, auto_t, 512, &threads);
+  if (rc != MCH_OK) return rc;
+  mch::WideArgs a;
+  a.pos_in = d->pos_in; a.pos_in_stride = d->pos_in_chain_stride; a.pos_out = d->pos_out;
+  a.C = d->n_chains; a.N = d->n_atoms; a.S = d->n_row_lists; a.B = d->n_bonds;
+  a.G = G; a.chunk = chunk; a.max_rows = d->max_rows;
+  a.perm = d->perm; a.bond_slot = d->bond_slots; a.bond_su = d->bond_su;
+  a.row_off = d->row_offsets; a.row_slot = d->row_slots; a.row_w = d->row_weights;
+  a.run_off = d->run_offsets; a.runs = d->runs;
+  a.p = to_params(d->params);
+  const int mk = mu_kind(d->params.nonbond_mu, &a.mu_int);
+  a.num_steps = d->num_steps < 1 ? 1 : d->num_steps;
+  a.rng = d->rng_state;
+  a.U = d->system_potential; a.Unb = d->nonbonded_potential; a.maxd = d->max_bond_distance;
+  a.n_accept = d->n_accepted; a.last_info = d->last_step_info;
+  a.trace_f = d->trace_potentials; a.trace_i = d->trace_info; a.traj = d->trajectory;
+  a.pairs = reinterpret_cast<unsigned long long*>(d->pair_evals);
+  a.inexact_undo = d->inexact_undo;
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  const bool io_f64 = d->io_dtype == MCH_F64;
+  return d->compute_dtype == MCH_F64 ? mch::launch_wide_f64(io_f64, mk, a, threads, smem, s)
+                                     : mch::launch_wide_f32(io_f64, mk, a, threads, smem, s);
+}
+}  // namespace
+
 int mch_optimize_batch(const mch_optimize_desc* d, void* stream) {
   if (!d) return fail(MCH_ERR_INVALID, "mch_optimize_batch: null descriptor");
   if (d->n_chains <= 0 || d->n_atoms <= 0 || d->n_subunits <= 0 || d->n_bonds <= 0 || d->max_subunit_atoms <= 0)
@@ -203,7 +259,10 @@ int mch_optimize_batch(const mch_optimize_desc* d, void* stream) {
   if (!d->pos_in || !d->pos_out || !d->perm || !d->su_offsets || !d->bonds || !d->bond_su || !d->rng_state ||
       !d->system_potential || !d->nonbonded_potential || !d->max_bond_distance || !d->n_accepted || !d->last_step_info)
     return fail(MCH_ERR_INVALID, "mch_optimize_batch: null required pointer");
+  if (d->general < 0 || d->general > 2) return fail(MCH_ERR_INVALID, "mch_optimize_batch: general must be 0, 1 or 2");
+  if (d->general != 0) return optimize_wide(d, stream);
   int smem = mch_optimize_smem_bytes(d->n_atoms, d->n_subunits, d->n_bonds, d->max_subunit_atoms, d->compute_dtype);
+  if (smem == MCH_ERR_TOO_LARGE && d->n_row_lists > 0) return optimize_wide(d, stream);  // does not fit one CTA
   if (smem < 0) return smem;
   // chains that are (or will be) resident together: a caller that cuts one batch into several
   // launches (BatchPlan's pipelined slices) says so, and every slice gets the batch's choices

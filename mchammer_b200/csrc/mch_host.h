@@ -7,6 +7,8 @@
 
 namespace mch {
 
+struct WideArgs;
+
 // printf-style message into the calling thread's error buffer; returns `code`.
 int fail(int code, const char* fmt, ...);
 
@@ -42,6 +44,20 @@ int launch_clustered(K kernel, const A& args, int blocks, int threads, int smem,
   if (e != cudaSuccess) return fail(-3, "%s: cluster launch (%d CTAs per chain) failed: %s", what, cluster, cudaGetErrorString(e));
   return 0;
 }
+
+// Same, allowing the non-portable cluster size 16.
+template <typename K, typename A>
+int launch_clustered_wide(K kernel, const A& args, int blocks, int threads, int smem, int cluster, cudaStream_t stream,
+                          const char* what) {
+  if (cluster > 8) {
+    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+    if (e != cudaSuccess) return fail(-3, "%s: cluster of %d CTAs not allowed: %s", what, cluster, cudaGetErrorString(e));
+  }
+  return launch_clustered(kernel, args, blocks, threads, smem, cluster, stream, what);
+}
+
+int launch_wide_f32(bool io_f64, int mu_kind, const WideArgs& a, int threads, int smem, cudaStream_t s);
+int launch_wide_f64(bool io_f64, int mu_kind, const WideArgs& a, int threads, int smem, cudaStream_t s);
 
 // Kernel-variant dispatch of the resident Metropolis kernel (one TU per compute type, so the
 // instantiations compile in parallel).  io_f64: element type of the position arrays.

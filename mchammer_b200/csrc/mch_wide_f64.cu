@@ -1,0 +1,10 @@
+// fp64-compute instantiations of the split-state / general-subunit Metropolis kernel.
+#include "mch_host.h"
+#include "mch_wide.cuh"
+
+namespace mch {
+int launch_wide_f64(bool io_f64, int mk, const WideArgs& a, int threads, int smem, cudaStream_t s) {
+  return io_f64 ? launch_wide_io<double, double>(mk, a, threads, smem, s)
+                : launch_wide_io<double, float>(mk, a, threads, smem, s);
+}
+}  // namespace mch

@@ -53,6 +53,13 @@ class DeviceTopology:
     bonds: object
     bond_su: object
     n_heavy: object
+    # explicit moving sets for the split-state kernel (csrc/mch_wide.cuh)
+    bond_slots: object = None
+    row_offsets: object = None
+    row_slots: object = None
+    row_weights: object = None
+    run_offsets: object = None
+    runs: object = None
 
 
 def upload_topology(topo: LoweredTopology, device=None) -> DeviceTopology:
@@ -62,10 +69,15 @@ def upload_topology(topo: LoweredTopology, device=None) -> DeviceTopology:
     def put(a):
         return torch.from_numpy(np.ascontiguousarray(a, dtype=np.int32)).to(dev)
 
+    slot_of = np.empty(topo.n_atoms, dtype=np.int64)
+    slot_of[topo.perm] = np.arange(topo.n_atoms)
     return DeviceTopology(
         host=topo, device=dev, perm=put(topo.perm), su_offsets=put(topo.su_offsets),
         bonds=put(topo.bonds.reshape(-1)), bond_su=put(topo.bond_su.reshape(-1)),
         n_heavy=put(topo.n_heavy),
+        bond_slots=put(slot_of[topo.bonds.reshape(-1)]) if topo.n_bonds else put(np.zeros(0)),
+        row_offsets=put(topo.row_offsets), row_slots=put(topo.row_slots), row_weights=put(topo.row_weights),
+        run_offsets=put(topo.run_offsets), runs=put(topo.runs.reshape(-1)),
     )
 
 
@@ -101,6 +113,7 @@ def optimize_on_device(
     out: OptimizeOutput | None = None,
     cluster_size: int = 0,
     resident_chains_hint: int = 0,
+    force_split_state: bool = False,
 ) -> OptimizeOutput:
     """Launch the resident Metropolis kernel for ``n_chains`` chains (asynchronous)."""
     torch = native.require_cuda()
@@ -166,6 +179,14 @@ def optimize_on_device(
         desc.n_accepted, desc.last_step_info = ptr(out.n_accepted), ptr(out.last_step_info)
         desc.trace_potentials, desc.trace_info = ptr(out.trace_potentials), ptr(out.trace_info)
         desc.trajectory, desc.pair_evals = ptr(out.trajectory), ptr(out.pair_evals)
+        # explicit moving sets: needed for overlapping subunits (general = 1) and used by the library on
+        # its own for molecules that do not fit one CTA; general = 2 forces the split-state kernel
+        desc.general = 2 if force_split_state else (1 if topo.general else 0)
+        desc.n_row_lists, desc.max_rows, desc.reserved = topo.n_user_subunits, topo.max_rows, 0
+        desc.bond_slots = ptr(dtopo.bond_slots)
+        desc.row_offsets, desc.row_slots = ptr(dtopo.row_offsets), ptr(dtopo.row_slots)
+        desc.row_weights = ptr(dtopo.row_weights)
+        desc.run_offsets, desc.runs = ptr(dtopo.run_offsets), ptr(dtopo.runs)
         stream = torch.cuda.current_stream(dev).cuda_stream
         native.check(lib.mch_optimize_batch(C.byref(desc), C.c_void_p(stream)), "mch_optimize_batch")
     return out

@@ -53,6 +53,9 @@ class OptimizeDesc(C.Structure):
         ("last_step_info", C.c_void_p),
         ("trace_potentials", C.c_void_p), ("trace_info", C.c_void_p),
         ("trajectory", C.c_void_p), ("pair_evals", C.c_void_p),
+        ("general", C.c_int32), ("n_row_lists", C.c_int32), ("max_rows", C.c_int32), ("reserved", C.c_int32),
+        ("bond_slots", C.c_void_p), ("row_offsets", C.c_void_p), ("row_slots", C.c_void_p),
+        ("row_weights", C.c_void_p), ("run_offsets", C.c_void_p), ("runs", C.c_void_p),
     ]
 
 

@@ -141,7 +141,7 @@ class Optimizer:
         dev = self._torch_device()
         topo = lower_topology(
             mol.get_num_atoms(), bond_pair_ids, subunits,
-            require_bond_subunits=self._num_steps > 1,
+            require_bond_subunits=self._num_steps > 1, allow_overlap=True,
         )
         dtopo = engine.upload_topology(topo, dev.index)
         pos = torch.from_numpy(mol.get_position_matrix()).to(dev)
@@ -248,7 +248,7 @@ class Optimizer:
         native.require_cuda()
         topo = lower_topology(
             mol.get_num_atoms(), bond_pair_ids, subunits,
-            require_bond_subunits=self._num_steps > 1,
+            require_bond_subunits=self._num_steps > 1, allow_overlap=True,
         )
         if devices is None:
             devices = [self._torch_device().index]
