@@ -139,7 +139,7 @@ typedef struct mch_collapse_desc {
   int32_t n_moving_subunits;  /* the first n_moving_subunits subunits are the caller's dict entries; a trailing
                                  group (atoms in no subunit) never moves, is not contact-tested and does not
                                  enter the step scales (collapser.py:56-82, :106-157).  0 = all n_subunits */
-  int32_t reserved;           /* 0                                                        */
+  int32_t n_heavy_total;      /* sum of n_heavy[] (sizes a shared-memory buffer); 0 = unknown, n_atoms is assumed */
   double step_size, distance_threshold;
   const void* pos_in;         /* [dev] [n_mol or 1][n_atoms][3]                           */
   int64_t pos_in_mol_stride;

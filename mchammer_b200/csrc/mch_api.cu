@@ -375,7 +375,8 @@ int mch_collapse_batch(const mch_collapse_desc* d, void* stream) {
   const int alone_threads = d->n_atoms <= 128 ? 32 : (d->n_atoms <= 512 ? 128 : 256);
   int rc = check_threads(d->threads_per_mol, d->n_mol <= sm_count() ? alone_threads : batch_threads, 256, &threads);
   if (rc != MCH_OK) return rc;
-  const mch::ColLayout L = mch::col_layout(d->n_atoms, d->n_subunits, d->n_bonds, d->compute_dtype == MCH_F64 ? 8 : 4);
+  const int nh_total = (d->n_heavy_total > 0 && d->n_heavy_total <= d->n_atoms) ? d->n_heavy_total : d->n_atoms;
+  const mch::ColLayout L = mch::col_layout(d->n_atoms, d->n_subunits, d->n_bonds, d->compute_dtype == MCH_F64 ? 8 : 4, nh_total);
   if (L.total > kMaxSmem) return fail(MCH_ERR_TOO_LARGE, "molecule needs %d B of shared memory (limit %d)", L.total, kMaxSmem);
   mch::ColArgs a;
   a.pos_in = d->pos_in; a.pos_in_stride = d->pos_in_mol_stride; a.pos_out = d->pos_out;
@@ -384,6 +385,7 @@ int mch_collapse_batch(const mch_collapse_desc* d, void* stream) {
   a.perm = d->perm; a.su_off = d->su_offsets; a.n_heavy = d->n_heavy; a.bonds = d->bonds;
   a.step_size = d->step_size; a.threshold = d->distance_threshold; a.scale_steps = d->scale_steps;
   a.max_steps = d->max_steps;
+  a.nh_total = nh_total;
   a.steps_run = d->steps_run; a.min_dist = d->min_distance; a.maxd_last = d->max_bond_distance; a.status = d->status;
   a.trace_maxd = d->trace_max_bond; a.traj = d->trajectory; a.trace_cap = d->trace_capacity;
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);

@@ -15,6 +15,16 @@
 // 128 columns x 32 rows that are dealt round-robin to the warps (equal cost per block, so
 // the triangle's imbalance disappears); a block entirely below every column's limit runs
 // without the per-pair "row belongs to an earlier subunit" predicate.  Rows are broadcast LDS.
+//
+// The contact test runs in two tiers.  Every step needs only the BOOLEAN "min distance <
+// threshold"; the exact minimum matters once, at the end (threshold/2 test, log).  So each step
+// first runs a FAST pass -- expanded-form squared distances (4 FP instructions per pair instead
+// of 6: rows are broadcast as one LDS.128 of (-2x', -2y', -2z', |p'|^2)), in fp32 on packed
+// FFMA2/FADD2, in fp64 with the running minimum kept on the HIGH WORD of r^2 only (one integer
+// min per pair instead of DSETP + two selects) -- whose result bounds the true minimum from both
+// sides; only when the threshold lies inside those bounds (never seen outside constructed cases)
+// does the EXACT pass (plain form, full-precision min: the arithmetic of round 1) decide, and the
+// exact pass also produces the reported minimum.  Results are therefore those of the exact pass.
 #pragma once
 
 #include "mch_device.cuh"
@@ -36,6 +46,7 @@ struct ColArgs {
   const int* bonds;    // [B][2] atom ids
   double step_size, threshold;
   int scale_steps;
+  int nh_total;         // non-H atoms of the molecule (sizes the row buffer of the fast contact pass)
   int max_steps;        // safety cap (the reference loops forever if nothing ever touches)
   int* steps_run;       // [C]
   double* min_dist;     // [C] value compared with threshold/2
@@ -46,15 +57,17 @@ struct ColArgs {
   int trace_cap;
 };
 
-struct ColLayout { int x, y, z, suof, qatom, hoff, loff, bslot, csum, vec, wsum, total; };
+struct ColLayout { int x, y, z, rows, suof, qatom, hoff, loff, bslot, csum, vec, wsum, total; };
 
-MCH_HD ColLayout col_layout(int N, int S, int B, int tsize) {
+MCH_HD ColLayout col_layout(int N, int S, int B, int tsize, int n_heavy_total) {
   ColLayout L;
   const int np = align_up(N, 8);
   int o = 0;
   L.x = o; o += np * tsize;
   L.y = o; o += np * tsize;
   L.z = o; o += np * tsize;
+  o = align_up(o, 32);
+  L.rows = o; o += align_up(n_heavy_total + 4, 4) * row_bytes(tsize);  // encoded heavy atoms (fast contact pass)
   L.suof = o; o += np * 4;    // internal slot -> subunit
   L.qatom = o; o += np * 4;   // internal slot -> atom id
   L.hoff = o; o += align_up(S + 1, 4) * 4;  // heavy atoms before subunit s (internal slots of its heavy atoms)
@@ -78,7 +91,7 @@ mch_collapse_kernel(const __grid_constant__ ColArgs a) {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int nt = blockDim.x, nwarps = nt >> 5;
   const int N = a.N, S = a.S, B = a.B;
-  const ColLayout L = col_layout(N, S, B, (int)sizeof(T));
+  const ColLayout L = col_layout(N, S, B, (int)sizeof(T), a.nh_total);
   T* X = reinterpret_cast<T*>(smem + L.x);
   T* Y = reinterpret_cast<T*>(smem + L.y);
   T* Z = reinterpret_cast<T*>(smem + L.z);
@@ -87,6 +100,7 @@ mch_collapse_kernel(const __grid_constant__ ColArgs a) {
   int* hoff = reinterpret_cast<int*>(smem + L.hoff);
   int* loff = reinterpret_cast<int*>(smem + L.loff);
   int* bslot = reinterpret_cast<int*>(smem + L.bslot);
+  Row4<T>* Qh = reinterpret_cast<Row4<T>*>(smem + L.rows);
   double* csum = reinterpret_cast<double*>(smem + L.csum);
   double* vec = reinterpret_cast<double*>(smem + L.vec);
   double* wsum = reinterpret_cast<double*>(smem + L.wsum);
@@ -141,9 +155,23 @@ mch_collapse_kernel(const __grid_constant__ ColArgs a) {
   }
   __syncthreads();
 
+  constexpr int CT = 128, RB = 32;  // block = 4 column units x 32 rows
+  constexpr bool kFast = sizeof(T) == 4;
+  // centre of the expanded encoding in fp64 mode: the start centroid of the contact-tested atoms
+  double cen_x = 0.0, cen_y = 0.0, cen_z = 0.0;
+  if (!kFast) {
+    double sx = 0.0, sy = 0.0, sz = 0.0;
+    for (int q = tid; q < nh; q += nt) { sx += (double)X[q]; sy += (double)Y[q]; sz += (double)Z[q]; }
+    sx = warp_sum(sx); sy = warp_sum(sy); sz = warp_sum(sz);
+    if (lane == 0) { wsum[warp] = sx; wsum[32 + warp] = sy; wsum[64 + warp] = sz; }
+    __syncthreads();
+    for (int w = 0; w < nwarps; ++w) { cen_x += wsum[w]; cen_y += wsum[32 + w]; cen_z += wsum[64 + w]; }
+    const double inv_nh = nh > 0 ? 1.0 / nh : 0.0;
+    cen_x *= inv_nh; cen_y *= inv_nh; cen_z *= inv_nh;
+    __syncthreads();
+  }
   // min over cross-subunit heavy pairs of r^2, as a distance (sqrt is monotone, so
   // min(dist) == sqrt(min r2) exactly)
-  constexpr int CT = 128, RB = 32;  // block = 4 column units x 32 rows
   auto min_cross_distance = [&]() -> double {
     T best = far_away<T>();
     const int n_ct = (nh + CT - 1) / CT;
@@ -204,6 +232,173 @@ mch_collapse_kernel(const __grid_constant__ ColArgs a) {
     return sqrt(r2);
   };
 
+  // ---- fast contact pass: bounds [lo2, hi2) on the minimum squared distance ------------------------
+  // Encoded rows Qh[q] of the contact-tested heavy atoms relative to `cen` (fp32: the frame is centred
+  // already; fp64: the start centroid).  Rebuilt by encode_heavy() after every change of positions.
+  const Centre<T> cen{(T)(kFast ? 0.0 : cen_x), (T)(kFast ? 0.0 : cen_y), (T)(kFast ? 0.0 : cen_z)};
+  // rmax2 = largest |p'|^2: the rounding error of an expanded-form r^2 is bounded by a few ulps of
+  // (|p_i'| + |p_j'|)^2 <= 4 rmax2, which sets the width of the "ask the exact pass" band below.
+  double rmax2 = 0.0;
+  auto encode_heavy = [&]() {
+    T big = (T)0;
+    for (int q = tid; q < nh; q += nt) {
+      const Row4<T> r = encode_row<T, true>(X[q], Y[q], Z[q], cen);
+      Qh[q] = r;
+      big = r.w > big ? r.w : big;
+    }
+    double b = warp_max((double)big);
+    __syncthreads();
+    if (lane == 0) wsum[warp] = b;
+    __syncthreads();
+    b = wsum[0];
+    for (int w = 1; w < nwarps; ++w) b = fmax(b, wsum[w]);
+    rmax2 = b;
+    __syncthreads();
+  };
+  auto fast_bounds = [&](double& lo2, double& hi2) {
+    constexpr int kHuge = 0x7fe00000;  // high word of a huge finite double
+    float bestf = 3.0e38f;
+    int besti = kHuge;
+    const int n_ct = (nh + CT - 1) / CT;
+    int task = 0;
+    for (int ct = 0; ct < n_ct; ++ct) {
+      const int q0 = ct * CT;
+      const int q_last = min(q0 + CT, nh) - 1;
+      const int lim_lo = hoff[suof[q0]], lim_hi = hoff[suof[q_last]];
+      const int n_rb = (lim_hi + RB - 1) / RB;
+      int rb = (warp - task % nwarps + nwarps) % nwarps;
+      task += n_rb;
+      if (rb >= n_rb) continue;
+      int lim[4];
+      if constexpr (kFast) {
+        f32x2 xj[2], yj[2], zj[2], cj[2];
+        float m[4];
+#pragma unroll
+        for (int kp = 0; kp < 2; ++kp) {
+          float x[2], y[2], z[2], c2[2];
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            const int q = q0 + 32 * (2 * kp + h) + lane;
+            const bool live = q < nh;
+            lim[2 * kp + h] = live ? hoff[suof[q]] : 0;
+            x[h] = live ? X[q] : 1.0e18f; y[h] = live ? Y[q] : 1.0e18f; z[h] = live ? Z[q] : 1.0e18f;
+            c2[h] = fmaf(z[h], z[h], fmaf(y[h], y[h], x[h] * x[h]));
+            m[2 * kp + h] = 3.0e38f;
+          }
+          xj[kp] = pack2(x[0], x[1]); yj[kp] = pack2(y[0], y[1]); zj[kp] = pack2(z[0], z[1]); cj[kp] = pack2(c2[0], c2[1]);
+        }
+        for (; rb < n_rb; rb += nwarps) {
+          const int i0 = rb * RB, i1 = min(i0 + RB, lim_hi);
+          if (i1 <= lim_lo) {  // every row is a partner of every column of the tile: no per-pair predicate
+#pragma unroll 4
+            for (int i = i0; i < i1; ++i) {
+              const Row4<float> q = Qh[i];
+#pragma unroll
+              for (int kp = 0; kp < 2; ++kp) {
+                const f32x2 r2 = fma2(zj[kp], pack2(q.z, q.z), fma2(yj[kp], pack2(q.y, q.y),
+                                 fma2(xj[kp], pack2(q.x, q.x), add2(cj[kp], pack2(q.w, q.w)))));
+                float a0, a1;
+                unpack2(r2, a0, a1);
+                m[2 * kp] = fminf(m[2 * kp], a0);
+                m[2 * kp + 1] = fminf(m[2 * kp + 1], a1);
+              }
+            }
+          } else {
+#pragma unroll 1
+            for (int i = i0; i < i1; ++i) {
+              const Row4<float> q = Qh[i];
+#pragma unroll
+              for (int kp = 0; kp < 2; ++kp) {
+                const f32x2 r2 = fma2(zj[kp], pack2(q.z, q.z), fma2(yj[kp], pack2(q.y, q.y),
+                                 fma2(xj[kp], pack2(q.x, q.x), add2(cj[kp], pack2(q.w, q.w)))));
+                float a0, a1;
+                unpack2(r2, a0, a1);
+                a0 = i < lim[2 * kp] ? a0 : 3.0e38f;
+                a1 = i < lim[2 * kp + 1] ? a1 : 3.0e38f;
+                m[2 * kp] = fminf(m[2 * kp], a0);
+                m[2 * kp + 1] = fminf(m[2 * kp + 1], a1);
+              }
+            }
+          }
+        }
+        bestf = fminf(bestf, fminf(fminf(m[0], m[1]), fminf(m[2], m[3])));
+      } else {
+        double xj[4], yj[4], zj[4], cj[4];
+        int mh[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const int q = q0 + 32 * k + lane;
+          const bool live = q < nh;
+          lim[k] = live ? hoff[suof[q]] : 0;
+          xj[k] = live ? (double)X[q] - (double)cen.x : 1.0e150;
+          yj[k] = live ? (double)Y[q] - (double)cen.y : 1.0e150;
+          zj[k] = live ? (double)Z[q] - (double)cen.z : 1.0e150;
+          cj[k] = fma(zj[k], zj[k], fma(yj[k], yj[k], xj[k] * xj[k]));
+          mh[k] = kHuge;
+        }
+        for (; rb < n_rb; rb += nwarps) {
+          const int i0 = rb * RB, i1 = min(i0 + RB, lim_hi);
+          if (i1 <= lim_lo) {
+#pragma unroll 2
+            for (int i = i0; i < i1; ++i) {
+              const Row4<double> q = reinterpret_cast<const Row4<double>*>(Qh)[i];
+#pragma unroll
+              for (int k = 0; k < 4; ++k) {
+                const double r2 = fma(zj[k], q.z, fma(yj[k], q.y, fma(xj[k], q.x, cj[k] + q.w)));
+                mh[k] = min(mh[k], __double2hiint(r2));  // positive doubles order like their high words
+              }
+            }
+          } else {
+#pragma unroll 1
+            for (int i = i0; i < i1; ++i) {
+              const Row4<double> q = reinterpret_cast<const Row4<double>*>(Qh)[i];
+#pragma unroll
+              for (int k = 0; k < 4; ++k) {
+                const double r2 = fma(zj[k], q.z, fma(yj[k], q.y, fma(xj[k], q.x, cj[k] + q.w)));
+                mh[k] = min(mh[k], i < lim[k] ? __double2hiint(r2) : kHuge);
+              }
+            }
+          }
+        }
+        besti = min(besti, min(min(mh[0], mh[1]), min(mh[2], mh[3])));
+      }
+    }
+    __syncthreads();
+    if constexpr (kFast) {
+      bestf = warp_min(bestf);
+      if (lane == 0) wsum[warp] = (double)bestf;
+    } else {
+#pragma unroll
+      for (int mm = 16; mm > 0; mm >>= 1) besti = min(besti, __shfl_xor_sync(0xffffffffu, besti, mm));
+      if (lane == 0) wsum[warp] = (double)besti;  // exact: |besti| < 2^31
+    }
+    __syncthreads();
+    double v = wsum[0];
+    for (int w = 1; w < nwarps; ++w) v = fmin(v, wsum[w]);
+    if constexpr (kFast) {
+      // fp32 expanded form: |error| <= 8 roundings of magnitude <= 4 rmax2 (2^-24 each) -> 2e-6 rmax2
+      const double band = 2.0e-6 * rmax2 + 1.0e-6 * v;
+      lo2 = v - band; hi2 = v + band;
+    } else {
+      const int h = (int)v;
+      if (h < 0) { lo2 = -1.0; hi2 = 1.0e300; return; }  // rounding made a tiny r^2 negative: let the exact pass decide
+      const double band = 4.0e-15 * rmax2;             // same bound with 2^-53 roundings
+      lo2 = __hiloint2double(h, 0) - band;             // the true minimum lies in [high word, next high word)
+      hi2 = __hiloint2double(h + 1, 0) + band;
+    }
+  };
+  // "min distance < threshold" and, if exact is needed anyway, the minimum itself (dmin < 0: not computed)
+  auto contact = [&](double& dmin) -> bool {
+    double lo2, hi2;
+    fast_bounds(lo2, hi2);
+    const double t2 = a.threshold * a.threshold;
+    dmin = -1.0;
+    if (lo2 >= t2 * (1.0 + 4.0e-16) && lo2 > 0.0) return false;   // certainly no contact
+    if (hi2 < t2 * (1.0 - 4.0e-16)) return true;                   // certainly a contact
+    dmin = min_cross_distance();                                    // the threshold lies inside the bounds
+    return dmin < a.threshold;
+  };
+
   // one collapse step (collapser.py:159-180) with the given signed step size
   auto do_step = [&](double step) {
     for (int s = warp; s < S; s += nwarps) {
@@ -243,6 +438,7 @@ mch_collapse_kernel(const __grid_constant__ ColArgs a) {
       Z[n] = (T)((double)Z[n] - vec[3 * s + 2]);
     }
     __syncthreads();
+    encode_heavy();
   };
 
   auto record = [&](int step) {  // step is 1-based; longest listed bond + optional frame
@@ -273,14 +469,17 @@ mch_collapse_kernel(const __grid_constant__ ColArgs a) {
   // ------------------------------------------------------------ the loop
   int step = 0, status = 0;
   if (tid == 0) a.maxd_last[c] = 0.0;
-  double dmin = min_cross_distance();
-  while (!(dmin < a.threshold)) {
+  encode_heavy();
+  double dmin;
+  bool touching = contact(dmin);
+  while (!touching) {
     if (step >= a.max_steps) { status = 1; break; }
     ++step;
     do_step(a.step_size);
     record(step);
-    dmin = min_cross_distance();
+    touching = contact(dmin);
   }
+  if (dmin < 0.0) dmin = min_cross_distance();  // the exact minimum is reported and tested against threshold / 2
   if (status == 0 && dmin < a.threshold / 2) {
     ++step;
     do_step(-(a.step_size / 2));

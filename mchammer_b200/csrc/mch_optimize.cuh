@@ -136,6 +136,56 @@ template <typename Tio> MCH_D void store_io(void* base, long long idx, double v)
   reinterpret_cast<Tio*>(base)[idx] = (Tio)v;
 }
 
+// A chain's start geometry is one contiguous run of 3 N values in HBM: it is staged with 16-byte
+// loads (double2 / float4), consecutive lanes taking consecutive vectors -- fully coalesced -- and
+// every value is scattered to its SoA slot through `inv` (atom id -> slot, in shared memory).  A
+// chain whose run does not start on a 16-byte boundary (odd N and odd chain index) falls back to
+// element loads.  fp32 compute works in a frame centred on the start geometry (translation
+// invariant path; keeps |coordinates| small): origin = centroid; fp64 keeps the caller's frame bit
+// for bit (origin = 0).  A real function, so that the step loop's code does not depend on it.
+template <typename T, typename Tio>
+__device__ __noinline__ void stage_positions(const Tio* __restrict__ chain_in, int N, const int* __restrict__ inv,
+                                             T* __restrict__ X, T* __restrict__ Y, T* __restrict__ Z,
+                                             double* __restrict__ wsum, double* __restrict__ origin) {
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nt = blockDim.x, nwarps = nt >> 5;
+  constexpr int VEC = 16 / (int)sizeof(Tio);
+  const int nvec = (reinterpret_cast<unsigned long long>(chain_in) & 15ULL) == 0ULL ? (3 * N) / VEC : 0;
+  auto for_each_value = [&](auto&& visit) {  // visit(element index in [0, 3N), value)
+    for (int v = tid; v < nvec; v += nt) {
+      if constexpr (VEC == 2) {
+        const double2 d = reinterpret_cast<const double2*>(chain_in)[v];
+        visit(2 * v, (double)d.x); visit(2 * v + 1, (double)d.y);
+      } else {
+        const float4 d = reinterpret_cast<const float4*>(chain_in)[v];
+        visit(4 * v, (double)d.x); visit(4 * v + 1, (double)d.y); visit(4 * v + 2, (double)d.z); visit(4 * v + 3, (double)d.w);
+      }
+    }
+    for (int e = nvec * VEC + tid; e < 3 * N; e += nt) visit(e, (double)chain_in[e]);
+  };
+  double ox = 0.0, oy = 0.0, oz = 0.0;
+  if (sizeof(T) == 4) {
+    double sx = 0.0, sy = 0.0, sz = 0.0;
+    for_each_value([&](int e, double v) {
+      const int comp = e - 3 * (e / 3);
+      sx += comp == 0 ? v : 0.0; sy += comp == 1 ? v : 0.0; sz += comp == 2 ? v : 0.0;
+    });
+    sx = warp_sum(sx); sy = warp_sum(sy); sz = warp_sum(sz);
+    __syncthreads();
+    if (lane == 0) { wsum[warp] = sx; wsum[32 + warp] = sy; wsum[64 + warp] = sz; }
+    __syncthreads();
+    for (int w = 0; w < nwarps; ++w) { ox += wsum[w]; oy += wsum[32 + w]; oz += wsum[64 + w]; }
+    ox /= N; oy /= N; oz /= N;
+  }
+  __syncthreads();
+  for_each_value([&](int e, double v) {
+    const int atom = e / 3, comp = e - 3 * atom, slot = inv[atom];
+    if (comp == 0) X[slot] = (T)(v - ox);
+    else if (comp == 1) Y[slot] = (T)(v - oy);
+    else Z[slot] = (T)(v - oz);
+  });
+  origin[0] = ox; origin[1] = oy; origin[2] = oz;
+}
+
 // Subunits up to this many atoms are re-summed one lane per subunit when the energy table is
 // refreshed; larger ones by the whole warp.
 constexpr int REGROUP_SMALL = 64;
@@ -205,29 +255,7 @@ mch_optimize_kernel(const __grid_constant__ OptArgs a) {
   // fp32 compute works in a frame centred on the start geometry (translation invariant
   // path; keeps |coordinates| small).  fp64 keeps the caller's frame bit for bit.
   double origin[3] = {0.0, 0.0, 0.0};  // prologue only; kept in ctl->origin afterwards
-  if (sizeof(T) == 4) {
-    double sx = 0.0, sy = 0.0, sz = 0.0;
-    for (int n = tid; n < N; n += nt) {
-      sx += load_io<Tio>(a.pos_in, in_base + 3LL * n + 0);
-      sy += load_io<Tio>(a.pos_in, in_base + 3LL * n + 1);
-      sz += load_io<Tio>(a.pos_in, in_base + 3LL * n + 2);
-    }
-    sx = warp_sum(sx); sy = warp_sum(sy); sz = warp_sum(sz);
-    __syncthreads();  // inv reads above are done before wsum/colsum reuse below
-    if (lane == 0) { wsum[warp] = sx; wsum[32 + warp] = sy; wsum[64 + warp] = sz; }
-    __syncthreads();
-    for (int w = 0; w < nwarps; ++w) {
-      origin[0] += wsum[w]; origin[1] += wsum[32 + w]; origin[2] += wsum[64 + w];
-    }
-    origin[0] /= N; origin[1] /= N; origin[2] /= N;
-  }
-  __syncthreads();
-  for (int n = tid; n < N; n += nt) {
-    const long long src = in_base + 3LL * a.perm[n];
-    X[n] = (T)(load_io<Tio>(a.pos_in, src + 0) - origin[0]);
-    Y[n] = (T)(load_io<Tio>(a.pos_in, src + 1) - origin[1]);
-    Z[n] = (T)(load_io<Tio>(a.pos_in, src + 2) - origin[2]);
-  }
+  stage_positions<T, Tio>(reinterpret_cast<const Tio*>(a.pos_in) + in_base, N, inv, X, Y, Z, wsum, origin);
   if (tid == 0) { ctl->origin[0] = origin[0]; ctl->origin[1] = origin[1]; ctl->origin[2] = origin[2]; }
   for (int k = tid; k < S * S; k += nt) E[k] = 0.0;
   for (int k = tid; k < S; k += nt) invn[k] = 1.0 / (double)(suoff[k + 1] - suoff[k]);

@@ -5,7 +5,11 @@
 // U = U_nb + sum_b eps_b (r_b - R_t)^2, plus the longest listed bond
 // (optimizer.py:174-183).  One CTA per molecule; atoms staged once into shared memory;
 // the N(N-1)/2 pairs are covered by row blocks of ROWB atoms swept against all later
-// atoms (cross part) and against themselves (strict lower triangle), both through
+// atoms (cross part) and against themselves (strict lower triangle).  Every WARP takes whole row
+// blocks (its own row buffer, blocks dealt boustrophedon so the shrinking column ranges balance)
+// and sweeps them alone: no block-wide barrier until the final reduction (the first version
+// gave every block to the whole CTA and spent 36 % of its warp time at the two barriers per block).
+// Both parts go through
 // pair_sweep.  The long-bond harmonic term is fused into the same launch.
 #pragma once
 
@@ -37,7 +41,7 @@ MCH_HD PotLayout pot_layout(int N, int tsize) {
   L.y = o; o += np * tsize;
   L.z = o; o += np * tsize;
   o = align_up(o, 32);
-  L.rows = o; o += (POT_ROWB + 4) * 4 * tsize;  // + far-away padding row + prefetch overrun
+  L.rows = o; o += 8 * (POT_ROWB + 2 + kRowSlack) * 4 * tsize;  // one buffer per warp (+ padding rows + prefetch overrun)
   L.wsum = o; o += 3 * 32 * 8;
   L.total = align_up(o, 16);
   return L;
@@ -86,24 +90,38 @@ mch_potential_kernel(const __grid_constant__ PotArgs a) {
   }
   __syncthreads();
 
+  // Expanded form in fp64 only: without subunit knowledge a row block is 64 arbitrary atoms, so its
+  // centroid can be a molecule radius away from both atoms of a close pair; the rounding noise
+  // eps (|p_i'| + |p_j'|)^2 / r^2 is harmless in fp64 (~1e-13) but not in fp32 (~1e-4 on the closest pairs).
+  constexpr bool kFast = sizeof(T) == 4;
+  constexpr bool kXF = !kFast && (MCH_XF64 != 0);
+  constexpr bool kX2 = false;
+  constexpr int kRot3 = 0;
   double mine = 0.0;
-  for (int r0 = 0; r0 < N; r0 += POT_ROWB) {
+  Row4<T>* Qw = Q + warp * (POT_ROWB + 2 + kRowSlack);  // this warp's row buffer
+  const int nblocks = (N + POT_ROWB - 1) / POT_ROWB;
+  for (int round = 0; round * nwarps < nblocks; ++round) {
+    // boustrophedon: round 0 deals blocks 0..W-1 to warps 0..W-1, round 1 deals W..2W-1 to warps W-1..0, ...
+    const int blk = round * nwarps + ((round & 1) ? nwarps - 1 - warp : warp);
+    if (blk >= nblocks) continue;
+    const int r0 = blk * POT_ROWB;
     const int nrows = (N - r0) < POT_ROWB ? (N - r0) : POT_ROWB;
-    const int nrows_padded = padded_rows(nrows);
-    for (int i = tid; i < nrows_padded; i += nt) {
-      Row4<T> q;
-      if (i < nrows) { q.x = X[r0 + i]; q.y = Y[r0 + i]; q.z = Z[r0 + i]; }
-      else { q.x = far_away<T>(); q.y = far_away<T>(); q.z = far_away<T>(); }
-      q.w = (T)0;
-      Q[i] = q;
+    const int nrows_padded = kRot3 ? padded_rows3(nrows) : padded_rows(nrows);
+    Centre<T> ctr{(T)0, (T)0, (T)0};
+    if (kXF) {  // centre of the expanded encoding: the block's centroid
+      double sx = 0.0, sy = 0.0, sz = 0.0;
+      for (int i = lane; i < nrows; i += 32) { sx += (double)X[r0 + i]; sy += (double)Y[r0 + i]; sz += (double)Z[r0 + i]; }
+      ctr.x = (T)(warp_sum(sx) / nrows); ctr.y = (T)(warp_sum(sy) / nrows); ctr.z = (T)(warp_sum(sz) / nrows);
     }
-    __syncthreads();
+    __syncwarp();  // the previous block's sweeps of this warp are done with Qw
+    for (int i = lane; i < nrows_padded; i += 32)
+      Qw[i] = i < nrows ? encode_row<T, kXF>(X[r0 + i], Y[r0 + i], Z[r0 + i], ctr) : padding_row<T, kXF>();
+    __syncwarp();
     const int r1 = r0 + nrows;
     Cols later{r1, r1, r1, N};
-    mine += pair_sweep<T, MUK, false, false>(Q, nrows_padded, X, Y, Z, (T*)nullptr, later, term);
+    mine += pair_sweep<T, MUK, false, false, kXF, kX2, kRot3>(Qw, nrows_padded, X, Y, Z, (T*)nullptr, later, term, ctr, 0, 0, 1, true);
     Cols own{r0, r1, r1, r1};
-    mine += pair_sweep<T, MUK, true, false>(Q, nrows, X, Y, Z, (T*)nullptr, own, term);
-    __syncthreads();
+    mine += pair_sweep<T, MUK, true, false, kXF, kX2>(Qw, nrows, X, Y, Z, (T*)nullptr, own, term, ctr, 0, 0, 1, true);
   }
   mine = warp_sum(mine);
   if (lane == 0) wsum[warp] = mine;

@@ -265,7 +265,7 @@ def collapse_on_device(
         d.scale_steps, d.max_steps = int(bool(scale_steps)), int(max_steps)
         d.trace_capacity, d.threads_per_mol = int(trace_capacity), int(threads_per_mol)
         # atoms outside every subunit form a trailing static group that the Collapser must leave alone
-        d.n_moving_subunits, d.reserved = topo.n_user_subunits, 0
+        d.n_moving_subunits, d.n_heavy_total = topo.n_user_subunits, int(topo.n_heavy.sum())
         d.step_size, d.distance_threshold = float(step_size), float(distance_threshold)
         d.pos_in = ptr(pos_in)
         d.pos_in_mol_stride = 0 if pos_in.shape[0] == 1 and n_mol > 1 else n * 3

@@ -64,7 +64,7 @@ class CollapseDesc(C.Structure):
         ("n_mol", C.c_int32), ("n_atoms", C.c_int32), ("n_subunits", C.c_int32),
         ("n_bonds", C.c_int32), ("io_dtype", C.c_int32), ("compute_dtype", C.c_int32),
         ("scale_steps", C.c_int32), ("max_steps", C.c_int32), ("trace_capacity", C.c_int32),
-        ("threads_per_mol", C.c_int32), ("n_moving_subunits", C.c_int32), ("reserved", C.c_int32),
+        ("threads_per_mol", C.c_int32), ("n_moving_subunits", C.c_int32), ("n_heavy_total", C.c_int32),
         ("step_size", C.c_double), ("distance_threshold", C.c_double),
         ("pos_in", C.c_void_p), ("pos_in_mol_stride", C.c_int64), ("pos_out", C.c_void_p),
         ("perm", C.c_void_p), ("su_offsets", C.c_void_p), ("n_heavy", C.c_void_p),

@@ -1,7 +1,7 @@
 """Collapser kernel alone, device resident: molecule-steps/s, contact-test pair rate and the
 fraction of the FP pipe peak (9 flops per pair: 3 sub + mul + 2 fma + compare-select).
 
-    python profiles/collapse_batch.py [n_mol]
+    python profiles/collapse_batch.py [n_mol [fp64|fp32]]
 """
 import ctypes as C
 import sys
@@ -32,7 +32,7 @@ def pipe_peak(code):
     return probes.pipe_peak(torch, code, dev) * 1e12
 
 
-for precision in ("fp64", "fp32"):
+for precision in ((sys.argv[2],) if len(sys.argv) > 2 else ("fp64", "fp32")):
     peak = pipe_peak(native.MCH_F64) if precision == "fp64" else max(pipe_peak(native.MCH_F32), pipe_peak(3))
     for threads in (0, 128, 256):
         out = engine.collapse_on_device(dtopo, pos, n_mol, 0.02, 1.5, True, precision, threads_per_mol=threads)
