@@ -83,8 +83,11 @@ MCH_HD ColLayout col_layout(int N, int S, int B, int tsize, int n_heavy_total) {
 
 #ifdef __CUDACC__
 
+// Register budget: fp32 molecules are small in shared memory (33 KB for a 1000-atom cage), so six
+// 128-thread blocks share an SM at 80 registers (no spills); fp64 fits four per SM by shared memory
+// anyway and keeps 128 registers.
 template <typename T, typename Tio>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, (sizeof(T) == 4 ? 3 : 2))
 mch_collapse_kernel(const __grid_constant__ ColArgs a) {
   extern __shared__ __align__(32) unsigned char smem[];
   const int c = blockIdx.x;
@@ -260,16 +263,22 @@ mch_collapse_kernel(const __grid_constant__ ColArgs a) {
     float bestf = 3.0e38f;
     int besti = kHuge;
     const int n_ct = (nh + CT - 1) / CT;
-    int task = 0;
+    int task0 = 0;
     for (int ct = 0; ct < n_ct; ++ct) {
+      // Partners of the tile's columns: rows [0, lim_lo) for every column (blocks of RB rows, no
+      // predicate), and the heavy atoms of the subunits s_lo .. s_hi-1, each of which is a partner of
+      // exactly the columns that belong to a LATER subunit -- one task per such subunit: its rows are
+      // swept without a predicate into a scratch minimum that is merged per column afterwards.
       const int q0 = ct * CT;
       const int q_last = min(q0 + CT, nh) - 1;
-      const int lim_lo = hoff[suof[q0]], lim_hi = hoff[suof[q_last]];
-      const int n_rb = (lim_hi + RB - 1) / RB;
-      int rb = (warp - task % nwarps + nwarps) % nwarps;
-      task += n_rb;
-      if (rb >= n_rb) continue;
-      int lim[4];
+      const int s_lo = suof[q0], s_hi = suof[q_last];
+      const int lim_lo = hoff[s_lo];
+      const int n_rb = (lim_lo + RB - 1) / RB;
+      const int n_task = n_rb + (s_hi - s_lo);
+      int task = (warp - task0 % nwarps + nwarps) % nwarps;  // this warp's tasks: task, task + nwarps, ...
+      task0 += n_task;
+      if (task >= n_task) continue;
+      int su[4];
       if constexpr (kFast) {
         f32x2 xj[2], yj[2], zj[2], cj[2];
         float m[4];
@@ -280,46 +289,34 @@ mch_collapse_kernel(const __grid_constant__ ColArgs a) {
           for (int h = 0; h < 2; ++h) {
             const int q = q0 + 32 * (2 * kp + h) + lane;
             const bool live = q < nh;
-            lim[2 * kp + h] = live ? hoff[suof[q]] : 0;
+            su[2 * kp + h] = live ? suof[q] : -1;
             x[h] = live ? X[q] : 1.0e18f; y[h] = live ? Y[q] : 1.0e18f; z[h] = live ? Z[q] : 1.0e18f;
             c2[h] = fmaf(z[h], z[h], fmaf(y[h], y[h], x[h] * x[h]));
             m[2 * kp + h] = 3.0e38f;
           }
           xj[kp] = pack2(x[0], x[1]); yj[kp] = pack2(y[0], y[1]); zj[kp] = pack2(z[0], z[1]); cj[kp] = pack2(c2[0], c2[1]);
         }
-        for (; rb < n_rb; rb += nwarps) {
-          const int i0 = rb * RB, i1 = min(i0 + RB, lim_hi);
-          if (i1 <= lim_lo) {  // every row is a partner of every column of the tile: no per-pair predicate
+        for (; task < n_task; task += nwarps) {
+          const bool edge = task >= n_rb;
+          const int u = s_lo + (task - n_rb);
+          const int i0 = edge ? hoff[u] : task * RB;
+          const int i1 = edge ? hoff[u + 1] : min(i0 + RB, lim_lo);
+          float mt[4] = {3.0e38f, 3.0e38f, 3.0e38f, 3.0e38f};
 #pragma unroll 4
-            for (int i = i0; i < i1; ++i) {
-              const Row4<float> q = Qh[i];
+          for (int i = i0; i < i1; ++i) {
+            const Row4<float> q = Qh[i];
 #pragma unroll
-              for (int kp = 0; kp < 2; ++kp) {
-                const f32x2 r2 = fma2(zj[kp], pack2(q.z, q.z), fma2(yj[kp], pack2(q.y, q.y),
-                                 fma2(xj[kp], pack2(q.x, q.x), add2(cj[kp], pack2(q.w, q.w)))));
-                float a0, a1;
-                unpack2(r2, a0, a1);
-                m[2 * kp] = fminf(m[2 * kp], a0);
-                m[2 * kp + 1] = fminf(m[2 * kp + 1], a1);
-              }
-            }
-          } else {
-#pragma unroll 1
-            for (int i = i0; i < i1; ++i) {
-              const Row4<float> q = Qh[i];
-#pragma unroll
-              for (int kp = 0; kp < 2; ++kp) {
-                const f32x2 r2 = fma2(zj[kp], pack2(q.z, q.z), fma2(yj[kp], pack2(q.y, q.y),
-                                 fma2(xj[kp], pack2(q.x, q.x), add2(cj[kp], pack2(q.w, q.w)))));
-                float a0, a1;
-                unpack2(r2, a0, a1);
-                a0 = i < lim[2 * kp] ? a0 : 3.0e38f;
-                a1 = i < lim[2 * kp + 1] ? a1 : 3.0e38f;
-                m[2 * kp] = fminf(m[2 * kp], a0);
-                m[2 * kp + 1] = fminf(m[2 * kp + 1], a1);
-              }
+            for (int kp = 0; kp < 2; ++kp) {
+              const f32x2 r2 = fma2(zj[kp], pack2(q.z, q.z), fma2(yj[kp], pack2(q.y, q.y),
+                               fma2(xj[kp], pack2(q.x, q.x), add2(cj[kp], pack2(q.w, q.w)))));
+              float a0, a1;
+              unpack2(r2, a0, a1);
+              mt[2 * kp] = fminf(mt[2 * kp], a0);
+              mt[2 * kp + 1] = fminf(mt[2 * kp + 1], a1);
             }
           }
+#pragma unroll
+          for (int k = 0; k < 4; ++k) m[k] = (!edge || su[k] > u) ? fminf(m[k], mt[k]) : m[k];
         }
         bestf = fminf(bestf, fminf(fminf(m[0], m[1]), fminf(m[2], m[3])));
       } else {
@@ -329,36 +326,30 @@ mch_collapse_kernel(const __grid_constant__ ColArgs a) {
         for (int k = 0; k < 4; ++k) {
           const int q = q0 + 32 * k + lane;
           const bool live = q < nh;
-          lim[k] = live ? hoff[suof[q]] : 0;
+          su[k] = live ? suof[q] : -1;
           xj[k] = live ? (double)X[q] - (double)cen.x : 1.0e150;
           yj[k] = live ? (double)Y[q] - (double)cen.y : 1.0e150;
           zj[k] = live ? (double)Z[q] - (double)cen.z : 1.0e150;
           cj[k] = fma(zj[k], zj[k], fma(yj[k], yj[k], xj[k] * xj[k]));
           mh[k] = kHuge;
         }
-        for (; rb < n_rb; rb += nwarps) {
-          const int i0 = rb * RB, i1 = min(i0 + RB, lim_hi);
-          if (i1 <= lim_lo) {
+        for (; task < n_task; task += nwarps) {
+          const bool edge = task >= n_rb;
+          const int u = s_lo + (task - n_rb);
+          const int i0 = edge ? hoff[u] : task * RB;
+          const int i1 = edge ? hoff[u + 1] : min(i0 + RB, lim_lo);
+          int mt[4] = {kHuge, kHuge, kHuge, kHuge};
 #pragma unroll 2
-            for (int i = i0; i < i1; ++i) {
-              const Row4<double> q = reinterpret_cast<const Row4<double>*>(Qh)[i];
+          for (int i = i0; i < i1; ++i) {
+            const Row4<double> q = reinterpret_cast<const Row4<double>*>(Qh)[i];
 #pragma unroll
-              for (int k = 0; k < 4; ++k) {
-                const double r2 = fma(zj[k], q.z, fma(yj[k], q.y, fma(xj[k], q.x, cj[k] + q.w)));
-                mh[k] = min(mh[k], __double2hiint(r2));  // positive doubles order like their high words
-              }
-            }
-          } else {
-#pragma unroll 1
-            for (int i = i0; i < i1; ++i) {
-              const Row4<double> q = reinterpret_cast<const Row4<double>*>(Qh)[i];
-#pragma unroll
-              for (int k = 0; k < 4; ++k) {
-                const double r2 = fma(zj[k], q.z, fma(yj[k], q.y, fma(xj[k], q.x, cj[k] + q.w)));
-                mh[k] = min(mh[k], i < lim[k] ? __double2hiint(r2) : kHuge);
-              }
+            for (int k = 0; k < 4; ++k) {
+              const double r2 = fma(zj[k], q.z, fma(yj[k], q.y, fma(xj[k], q.x, cj[k] + q.w)));
+              mt[k] = min(mt[k], __double2hiint(r2));  // positive doubles order like their high words
             }
           }
+#pragma unroll
+          for (int k = 0; k < 4; ++k) mh[k] = (!edge || su[k] > u) ? min(mh[k], mt[k]) : mh[k];
         }
         besti = min(besti, min(min(mh[0], mh[1]), min(mh[2], mh[3])));
       }
