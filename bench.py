@@ -270,12 +270,12 @@ def measured_peaks():
 
 def profiled_traffic(precision: str):
     """DRAM bytes per launch of the dominant kernel from the committed `ncu --set full` summary."""
-    name = "r01_ncu_full_fp32.json" if precision == "fp32" else "r01_ncu_full_fp64.json"
-    path = os.path.join(REPO, "profiles", name)
-    if not os.path.exists(path):
-        return None
-    with open(path) as fh:
-        return json.load(fh).get("dram_bytes_per_launch")
+    for rnd in ("r02", "r01"):  # latest committed capture first
+        path = os.path.join(REPO, "profiles", f"{rnd}_ncu_full_{precision}.json")
+        if os.path.exists(path):
+            with open(path) as fh:
+                return json.load(fh).get("dram_bytes_per_launch")
+    return None
 
 
 def probe_pipe_peak(torch, dtype_code: int, device) -> float:
@@ -314,7 +314,7 @@ def secondary_lines(torch, dist, device, world: int, rank: int, flush, main_valu
     """The other numbers BASELINE.json's metric names, measured in this same run, device resident,
     CUDA events, max over ranks (every rank runs them; rank 0 reports):
       fp64         parity mode on the headline workload (cube1000, 4096 chains/GPU, num_steps 500)
-      m12l24_fp32  BASELINE configs[4] geometry, 1024 chains/GPU (8192/GPU on 8 GPUs = the 65,536-chain batch)
+      m12l24_fp32  BASELINE configs[4]: 65,536 chains of the 5004-atom cage in all, 65,536 / world per GPU (strong)
       strong_4096  the FIXED 4096-chain cube1000 batch split over the ranks (strong scaling)
     """
     import mchammer_b200 as mch
@@ -355,8 +355,9 @@ def secondary_lines(torch, dist, device, world: int, rank: int, flush, main_valu
         "roofline": {"bound": "fp64_pipe", "achieved": ach, "peak": peak64, "unit": "TFLOP/s",
                      "frac": ach / peak64 if peak64 else None},
     }
-    # --- M12L24 (BASELINE configs[4]): 65,536 chains over 8 GPUs = 8192 per GPU; 1024 per GPU otherwise
-    m_chains = 8192 if world == 8 else 1024
+    # --- M12L24 (BASELINE configs[4]): the FIXED 65,536-chain batch split over the ranks
+    # (65,536 on one GPU ... 8192 per GPU on 8; final geometries of one GPU's share: 7.9 GB at N=1)
+    m_chains = 65536 // world
     m_steps = WORKLOADS["m12l24"]["num_steps"]
     sec, pairs, n_atoms = resident("m12l24", m_chains, m_steps, "fp32", 2)
     peak32 = None
@@ -368,6 +369,7 @@ def secondary_lines(torch, dist, device, world: int, rank: int, flush, main_valu
                     f"num_steps={m_steps} (reduced from 500, BASELINE configs[4] allows it), fast mode",
         "value": m_chains * world * (m_steps - 1) / sec, "unit": UNIT, "ms_per_launch": 1e3 * sec,
         "pair_evals_per_s": pairs * world / sec,
+        "scaling": "strong",
         "roofline": {"bound": "fp32_pipe", "achieved": ach, "peak": peak32, "unit": "TFLOP/s",
                      "frac": ach / peak32 if peak32 else None},
     }
