@@ -16,15 +16,15 @@
 // the triangle's imbalance disappears); a block entirely below every column's limit runs
 // without the per-pair "row belongs to an earlier subunit" predicate.  Rows are broadcast LDS.
 //
-// The contact test runs in two tiers.  Every step needs only the BOOLEAN "min distance <
-// threshold"; the exact minimum matters once, at the end (threshold/2 test, log).  So each step
-// first runs a FAST pass -- expanded-form squared distances (4 FP instructions per pair instead
-// of 6: rows are broadcast as one LDS.128 of (-2x', -2y', -2z', |p'|^2)), in fp32 on packed
-// FFMA2/FADD2, in fp64 with the running minimum kept on the HIGH WORD of r^2 only (one integer
-// min per pair instead of DSETP + two selects) -- whose result bounds the true minimum from both
-// sides; only when the threshold lies inside those bounds (never seen outside constructed cases)
-// does the EXACT pass (plain form, full-precision min: the arithmetic of round 1) decide, and the
-// exact pass also produces the reported minimum.  Results are therefore those of the exact pass.
+// The contact test needs, per step, only the BOOLEAN "min distance < threshold"; the exact minimum
+// matters once, at the end (threshold/2 test, log).  Every pass runs in a FAST form -- expanded-form
+// squared distances (4 FP instructions per pair instead of 6: rows are broadcast as one LDS.128 of
+// (-2x', -2y', -2z', |p'|^2)), in fp32 on packed FFMA2/FADD2, in fp64 with the running minimum kept on
+// the HIGH WORD of r^2 only (one integer min per pair instead of DSETP + two selects).  A (row block,
+// column) whose fast minimum lies under threshold^2 + the fast form's error bound is a candidate and is
+// re-evaluated on the spot in the plain form at full precision (the arithmetic of round 1); every pair
+// under the threshold is a candidate, so the decision and the reported minimum are those of the plain
+// form -- and a pass without a contact has no candidates: there is no separate exact pass any more.
 #pragma once
 
 #include "mch_device.cuh"
@@ -235,7 +235,7 @@ mch_collapse_kernel(const __grid_constant__ ColArgs a) {
     return sqrt(r2);
   };
 
-  // ---- fast contact pass: bounds [lo2, hi2) on the minimum squared distance ------------------------
+  // ---- contact pass ------------------------------------------------------------------------------
   // Encoded rows Qh[q] of the contact-tested heavy atoms relative to `cen` (fp32: the frame is centred
   // already; fp64: the start centroid).  Rebuilt by encode_heavy() after every change of positions.
   const Centre<T> cen{(T)(kFast ? 0.0 : cen_x), (T)(kFast ? 0.0 : cen_y), (T)(kFast ? 0.0 : cen_z)};
@@ -258,17 +258,29 @@ mch_collapse_kernel(const __grid_constant__ ColArgs a) {
     rmax2 = b;
     __syncthreads();
   };
-  auto fast_bounds = [&](double& lo2, double& hi2) {
-    constexpr int kHuge = 0x7fe00000;  // high word of a huge finite double
-    float bestf = 3.0e38f;
-    int besti = kHuge;
+  // One pass over all cross-subunit heavy pairs in the fast form.  Every (task, column) whose fast minimum
+  // lies under `cut` = threshold^2 + the fast form's error bound is a CANDIDATE: its rows are evaluated once
+  // more in the plain form (round 1's arithmetic, full precision) and folded into the exact minimum `em`.
+  // A pair whose exact r^2 is under threshold^2 is always a candidate, so
+  //   * "min distance < threshold"  ==  sqrt(em) < threshold, the decision of the plain-form pass, and
+  //   * when that holds, em IS the exact global minimum (reported, tested against threshold / 2).
+  // Without a contact there are no candidates (or a handful inside the error band) and the pass costs
+  // nothing beyond the fast form: no second pass, no running global minimum.
+  auto contact_pass = [&]() -> double {
+    const double t2 = a.threshold * a.threshold;
+    // fp32 expanded form: |error| <= 8 roundings of magnitude <= 4 rmax2 (2^-24 each) -> 2e-6 rmax2;
+    // fp64: the same bound with 2^-53 roundings, plus the high-word granularity (2^-20 relative)
+    const double cut = kFast ? t2 * (1.0 + 2.0e-6) + 2.0e-6 * rmax2 : t2 * (1.0 + 2.0e-6) + 4.0e-15 * rmax2;
+    const float cutf = (float)cut * (1.0f + 1.0e-6f);
+    const int cuti = __double2hiint(cut);
+    T em = far_away<T>() * far_away<T>();
     const int n_ct = (nh + CT - 1) / CT;
     int task0 = 0;
     for (int ct = 0; ct < n_ct; ++ct) {
       // Partners of the tile's columns: rows [0, lim_lo) for every column (blocks of RB rows, no
       // predicate), and the heavy atoms of the subunits s_lo .. s_hi-1, each of which is a partner of
       // exactly the columns that belong to a LATER subunit -- one task per such subunit: its rows are
-      // swept without a predicate into a scratch minimum that is merged per column afterwards.
+      // swept without a predicate; which columns they count for is decided per task afterwards.
       const int q0 = ct * CT;
       const int q_last = min(q0 + CT, nh) - 1;
       const int s_lo = suof[q0], s_hi = suof[q_last];
@@ -279,9 +291,17 @@ mch_collapse_kernel(const __grid_constant__ ColArgs a) {
       task0 += n_task;
       if (task >= n_task) continue;
       int su[4];
+      // the plain-form re-evaluation of one candidate (task rows [i0, i1), this lane's column k)
+      auto refine = [&](int k, int i0, int i1) {
+        const int q = q0 + 32 * k + lane;
+        const T xq = X[q], yq = Y[q], zq = Z[q];
+        for (int i = i0; i < i1; ++i) {
+          const T dx = xq - X[i], dy = yq - Y[i], dz = zq - Z[i];
+          em = min(em, fma(dz, dz, fma(dy, dy, dx * dx)));
+        }
+      };
       if constexpr (kFast) {
         f32x2 xj[2], yj[2], zj[2], cj[2];
-        float m[4];
 #pragma unroll
         for (int kp = 0; kp < 2; ++kp) {
           float x[2], y[2], z[2], c2[2];
@@ -292,7 +312,6 @@ mch_collapse_kernel(const __grid_constant__ ColArgs a) {
             su[2 * kp + h] = live ? suof[q] : -1;
             x[h] = live ? X[q] : 1.0e18f; y[h] = live ? Y[q] : 1.0e18f; z[h] = live ? Z[q] : 1.0e18f;
             c2[h] = fmaf(z[h], z[h], fmaf(y[h], y[h], x[h] * x[h]));
-            m[2 * kp + h] = 3.0e38f;
           }
           xj[kp] = pack2(x[0], x[1]); yj[kp] = pack2(y[0], y[1]); zj[kp] = pack2(z[0], z[1]); cj[kp] = pack2(c2[0], c2[1]);
         }
@@ -316,12 +335,11 @@ mch_collapse_kernel(const __grid_constant__ ColArgs a) {
             }
           }
 #pragma unroll
-          for (int k = 0; k < 4; ++k) m[k] = (!edge || su[k] > u) ? fminf(m[k], mt[k]) : m[k];
+          for (int k = 0; k < 4; ++k)
+            if (mt[k] <= cutf && (edge ? su[k] > u : su[k] >= 0)) refine(k, i0, i1);
         }
-        bestf = fminf(bestf, fminf(fminf(m[0], m[1]), fminf(m[2], m[3])));
       } else {
         double xj[4], yj[4], zj[4], cj[4];
-        int mh[4];
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
           const int q = q0 + 32 * k + lane;
@@ -331,13 +349,13 @@ mch_collapse_kernel(const __grid_constant__ ColArgs a) {
           yj[k] = live ? (double)Y[q] - (double)cen.y : 1.0e150;
           zj[k] = live ? (double)Z[q] - (double)cen.z : 1.0e150;
           cj[k] = fma(zj[k], zj[k], fma(yj[k], yj[k], xj[k] * xj[k]));
-          mh[k] = kHuge;
         }
         for (; task < n_task; task += nwarps) {
           const bool edge = task >= n_rb;
           const int u = s_lo + (task - n_rb);
           const int i0 = edge ? hoff[u] : task * RB;
           const int i1 = edge ? hoff[u + 1] : min(i0 + RB, lim_lo);
+          constexpr int kHuge = 0x7fe00000;  // high word of a huge finite double
           int mt[4] = {kHuge, kHuge, kHuge, kHuge};
 #pragma unroll 2
           for (int i = i0; i < i1; ++i) {
@@ -346,48 +364,28 @@ mch_collapse_kernel(const __grid_constant__ ColArgs a) {
             for (int k = 0; k < 4; ++k) {
               const double r2 = fma(zj[k], q.z, fma(yj[k], q.y, fma(xj[k], q.x, cj[k] + q.w)));
               mt[k] = min(mt[k], __double2hiint(r2));  // positive doubles order like their high words
-            }
+            }                                          // (a tiny r^2 rounded negative has a negative high word)
           }
 #pragma unroll
-          for (int k = 0; k < 4; ++k) mh[k] = (!edge || su[k] > u) ? min(mh[k], mt[k]) : mh[k];
+          for (int k = 0; k < 4; ++k)
+            if (mt[k] <= cuti && (edge ? su[k] > u : su[k] >= 0)) refine(k, i0, i1);
         }
-        besti = min(besti, min(min(mh[0], mh[1]), min(mh[2], mh[3])));
       }
     }
+    em = warp_min(em);
     __syncthreads();
-    if constexpr (kFast) {
-      bestf = warp_min(bestf);
-      if (lane == 0) wsum[warp] = (double)bestf;
-    } else {
-#pragma unroll
-      for (int mm = 16; mm > 0; mm >>= 1) besti = min(besti, __shfl_xor_sync(0xffffffffu, besti, mm));
-      if (lane == 0) wsum[warp] = (double)besti;  // exact: |besti| < 2^31
-    }
+    if (lane == 0) wsum[warp] = (double)em;
     __syncthreads();
     double v = wsum[0];
     for (int w = 1; w < nwarps; ++w) v = fmin(v, wsum[w]);
-    if constexpr (kFast) {
-      // fp32 expanded form: |error| <= 8 roundings of magnitude <= 4 rmax2 (2^-24 each) -> 2e-6 rmax2
-      const double band = 2.0e-6 * rmax2 + 1.0e-6 * v;
-      lo2 = v - band; hi2 = v + band;
-    } else {
-      const int h = (int)v;
-      if (h < 0) { lo2 = -1.0; hi2 = 1.0e300; return; }  // rounding made a tiny r^2 negative: let the exact pass decide
-      const double band = 4.0e-15 * rmax2;             // same bound with 2^-53 roundings
-      lo2 = __hiloint2double(h, 0) - band;             // the true minimum lies in [high word, next high word)
-      hi2 = __hiloint2double(h + 1, 0) + band;
-    }
+    return v;  // exact minimum r^2 over the candidates (huge if there is none)
   };
-  // "min distance < threshold" and, if exact is needed anyway, the minimum itself (dmin < 0: not computed)
+  // "min distance < threshold"; when true, dmin is the exact minimum distance (dmin < 0: not computed)
   auto contact = [&](double& dmin) -> bool {
-    double lo2, hi2;
-    fast_bounds(lo2, hi2);
-    const double t2 = a.threshold * a.threshold;
-    dmin = -1.0;
-    if (lo2 >= t2 * (1.0 + 4.0e-16) && lo2 > 0.0) return false;   // certainly no contact
-    if (hi2 < t2 * (1.0 - 4.0e-16)) return true;                   // certainly a contact
-    dmin = min_cross_distance();                                    // the threshold lies inside the bounds
-    return dmin < a.threshold;
+    const double d = sqrt(contact_pass());
+    const bool touching = d < a.threshold;
+    dmin = touching ? d : -1.0;
+    return touching;
   };
 
   // one collapse step (collapser.py:159-180) with the given signed step size

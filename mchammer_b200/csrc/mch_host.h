@@ -66,11 +66,16 @@ int launch_optimize_f64(bool io_f64, int mu_kind, const OptArgs& a, int threads,
 
 template <typename T, typename Tio, int NTMAX>
 int launch_optimize_nt(int mk, const OptArgs& a, int threads, int smem, cudaStream_t s) {
+#ifdef MCH_QUICK  // tuning builds (profiles/quick_variant.sh): mu = 3 only, seconds instead of minutes
+  if (mk != MU_3) return fail(-3, "MCH_QUICK build: mu = 3 only");
+  return launch(mch_optimize_kernel<T, Tio, MU_3, NTMAX>, a, a.C, threads, smem, s, "mch_optimize_batch");
+#else
   switch (mk) {
     case MU_3: return launch(mch_optimize_kernel<T, Tio, MU_3, NTMAX>, a, a.C, threads, smem, s, "mch_optimize_batch");
     case MU_INT: return launch(mch_optimize_kernel<T, Tio, MU_INT, NTMAX>, a, a.C, threads, smem, s, "mch_optimize_batch");
     default: return launch(mch_optimize_kernel<T, Tio, MU_REAL, NTMAX>, a, a.C, threads, smem, s, "mch_optimize_batch");
   }
+#endif
 }
 
 // a chain spread over a.cluster CTAs: the large-block instantiation, cluster-capable
@@ -78,11 +83,16 @@ template <typename T, typename Tio>
 int launch_optimize_cluster(int mk, const OptArgs& a, int threads, int smem, cudaStream_t s) {
   constexpr int NT = 512;  // latency case: 512 threads at 128 registers in both precisions (no spills in the control section)
   const int blocks = a.C * a.cluster;
+#ifdef MCH_QUICK
+  if (mk != MU_3) return fail(-3, "MCH_QUICK build: mu = 3 only");
+  return launch_clustered(mch_optimize_kernel<T, Tio, MU_3, NT, true>, a, blocks, threads, smem, a.cluster, s, "mch_optimize_batch");
+#else
   switch (mk) {
     case MU_3: return launch_clustered(mch_optimize_kernel<T, Tio, MU_3, NT, true>, a, blocks, threads, smem, a.cluster, s, "mch_optimize_batch");
     case MU_INT: return launch_clustered(mch_optimize_kernel<T, Tio, MU_INT, NT, true>, a, blocks, threads, smem, a.cluster, s, "mch_optimize_batch");
     default: return launch_clustered(mch_optimize_kernel<T, Tio, MU_REAL, NT, true>, a, blocks, threads, smem, a.cluster, s, "mch_optimize_batch");
   }
+#endif
 }
 
 template <typename T, typename Tio>

@@ -449,24 +449,28 @@ mch_optimize_kernel(const __grid_constant__ OptArgs a) {
     const int side = (int)pcg_bounded(rng, 2u);                    // :225
     ms = bsu[2 * kb + side];
     const double rnd = (pcg_double(rng) - 0.5) * 2.0;              // :229
-    // subunit centroid minus molecule centroid                    // :236-237
-    double cvx, cvy, cvz;
-    if (kFast) {
-      const double in = invn[ms], iN = 1.0 / (double)N;
-      cvx = csum[3 * ms] * in - ctot[0] * iN;
-      cvy = csum[3 * ms + 1] * in - ctot[1] * iN;
-      cvz = csum[3 * ms + 2] * in - ctot[2] * iN;
-    } else {
-      const double nms = (double)(suoff[ms + 1] - suoff[ms]);
-      cvx = csum[3 * ms] / nms - ctot[0] / N;
-      cvy = csum[3 * ms + 1] / nms - ctot[1] / N;
-      cvz = csum[3 * ms + 2] / nms - ctot[2] / N;
-    }
     kind = (int)pcg_bounded(rng, 2u);                              // :242-244
     const double ss = a.p.step_size;
     double vx, vy, vz;
-    if (kind == 0) { vx = ((-bvx) * ss) * rnd; vy = ((-bvy) * ss) * rnd; vz = ((-bvz) * ss) * rnd; }   // :233
-    else           { vx = (cvx * ss) * rnd;    vy = (cvy * ss) * rnd;    vz = (cvz * ss) * rnd; }      // :238
+    if (kind == 0) {                                               // :233
+      vx = ((-bvx) * ss) * rnd; vy = ((-bvy) * ss) * rnd; vz = ((-bvz) * ss) * rnd;
+    } else {
+      // subunit centroid minus molecule centroid (:236-238) -- formed only when the draw asks for it
+      // (warp-uniform branch; in fp64 these are six divisions)
+      double cvx, cvy, cvz;
+      if (kFast) {
+        const double in = invn[ms], iN = 1.0 / (double)N;
+        cvx = csum[3 * ms] * in - ctot[0] * iN;
+        cvy = csum[3 * ms + 1] * in - ctot[1] * iN;
+        cvz = csum[3 * ms + 2] * in - ctot[2] * iN;
+      } else {
+        const double nms = (double)(suoff[ms + 1] - suoff[ms]);
+        cvx = csum[3 * ms] / nms - ctot[0] / N;
+        cvy = csum[3 * ms + 1] / nms - ctot[1] / N;
+        cvz = csum[3 * ms + 2] / nms - ctot[2] / N;
+      }
+      vx = (cvx * ss) * rnd; vy = (cvy * ss) * rnd; vz = (cvz * ss) * rnd;
+    }
     tvx = (T)vx; tvy = (T)vy; tvz = (T)vz;
     const int n = fill_rows(ms, tvx, tvy, tvz);                    // :248-252  (pos - vector)
     if (lane == 0) {
