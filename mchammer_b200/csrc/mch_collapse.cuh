@@ -240,7 +240,12 @@ mch_collapse_kernel(const __grid_constant__ ColArgs a) {
   // already; fp64: the start centroid).  Rebuilt by encode_heavy() after every change of positions.
   const Centre<T> cen{(T)(kFast ? 0.0 : cen_x), (T)(kFast ? 0.0 : cen_y), (T)(kFast ? 0.0 : cen_z)};
   // rmax2 = largest |p'|^2: the rounding error of an expanded-form r^2 is bounded by a few ulps of
-  // (|p_i'| + |p_j'|)^2 <= 4 rmax2, which sets the width of the "ask the exact pass" band below.
+  // (|p_i'| + |p_j'|)^2 <= 4 rmax2, which sets the width of the candidate band below.
+  // The per-pair work of the pass is r^2 - |p_j'|^2 = fma(z_j', qz, fma(y_j', qy, fma(x_j', qx, qw))) -- the
+  // column's own |p_j'|^2 is the same for every row, so it is taken out of the minimum (3 FP instructions per
+  // pair; it comes back in the per-column candidate threshold).  fp64 keeps its minimum on the HIGH WORD,
+  // which orders positive doubles only: there the rows carry qw = |p_i'|^2 + bias with bias = rmax2 >= every
+  // |p_j'|^2, so every value stays positive.
   double rmax2 = 0.0;
   auto encode_heavy = [&]() {
     T big = (T)0;
@@ -249,14 +254,16 @@ mch_collapse_kernel(const __grid_constant__ ColArgs a) {
       Qh[q] = r;
       big = r.w > big ? r.w : big;
     }
-    double b = warp_max((double)big);
+    const double bw = warp_max((double)big);
+    if (lane == 0) wsum[32 + warp] = bw;  // (slots [32, 64): last read before the previous barrier pair)
     __syncthreads();
-    if (lane == 0) wsum[warp] = b;
-    __syncthreads();
-    b = wsum[0];
-    for (int w = 1; w < nwarps; ++w) b = fmax(b, wsum[w]);
+    double b = wsum[32];
+    for (int w = 1; w < nwarps; ++w) b = fmax(b, wsum[32 + w]);
     rmax2 = b;
-    __syncthreads();
+    if (!kFast) {  // every thread biases the rows it wrote itself
+      for (int q = tid; q < nh; q += nt) Qh[q].w += (T)b;
+      __syncthreads();
+    }
   };
   // One pass over all cross-subunit heavy pairs in the fast form.  Every (task, column) whose fast minimum
   // lies under `cut` = threshold^2 + the fast form's error bound is a CANDIDATE: its rows are evaluated once
@@ -270,9 +277,8 @@ mch_collapse_kernel(const __grid_constant__ ColArgs a) {
     const double t2 = a.threshold * a.threshold;
     // fp32 expanded form: |error| <= 8 roundings of magnitude <= 4 rmax2 (2^-24 each) -> 2e-6 rmax2;
     // fp64: the same bound with 2^-53 roundings, plus the high-word granularity (2^-20 relative)
-    const double cut = kFast ? t2 * (1.0 + 2.0e-6) + 2.0e-6 * rmax2 : t2 * (1.0 + 2.0e-6) + 4.0e-15 * rmax2;
-    const float cutf = (float)cut * (1.0f + 1.0e-6f);
-    const int cuti = __double2hiint(cut);
+    const double cut = kFast ? t2 * (1.0 + 2.0e-6) + 2.0e-6 * rmax2 : t2 * (1.0 + 2.0e-6) + 1.0e-14 * rmax2;
+    const double bias = kFast ? 0.0 : rmax2;  // see encode_heavy
     T em = far_away<T>() * far_away<T>();
     const int n_ct = (nh + CT - 1) / CT;
     int task0 = 0;
@@ -301,19 +307,21 @@ mch_collapse_kernel(const __grid_constant__ ColArgs a) {
         }
       };
       if constexpr (kFast) {
-        f32x2 xj[2], yj[2], zj[2], cj[2];
+        f32x2 xj[2], yj[2], zj[2];
+        float cutk[4];
 #pragma unroll
         for (int kp = 0; kp < 2; ++kp) {
-          float x[2], y[2], z[2], c2[2];
+          float x[2], y[2], z[2];
 #pragma unroll
           for (int h = 0; h < 2; ++h) {
             const int q = q0 + 32 * (2 * kp + h) + lane;
             const bool live = q < nh;
             su[2 * kp + h] = live ? suof[q] : -1;
             x[h] = live ? X[q] : 1.0e18f; y[h] = live ? Y[q] : 1.0e18f; z[h] = live ? Z[q] : 1.0e18f;
-            c2[h] = fmaf(z[h], z[h], fmaf(y[h], y[h], x[h] * x[h]));
+            // candidate threshold of this column: r^2 - |p_j'|^2 <= cut - |p_j'|^2 (rounded up)
+            cutk[2 * kp + h] = ((float)cut - fmaf(z[h], z[h], fmaf(y[h], y[h], x[h] * x[h]))) + 1.0e-6f * (float)cut;
           }
-          xj[kp] = pack2(x[0], x[1]); yj[kp] = pack2(y[0], y[1]); zj[kp] = pack2(z[0], z[1]); cj[kp] = pack2(c2[0], c2[1]);
+          xj[kp] = pack2(x[0], x[1]); yj[kp] = pack2(y[0], y[1]); zj[kp] = pack2(z[0], z[1]);
         }
         for (; task < n_task; task += nwarps) {
           const bool edge = task >= n_rb;
@@ -327,7 +335,7 @@ mch_collapse_kernel(const __grid_constant__ ColArgs a) {
 #pragma unroll
             for (int kp = 0; kp < 2; ++kp) {
               const f32x2 r2 = fma2(zj[kp], pack2(q.z, q.z), fma2(yj[kp], pack2(q.y, q.y),
-                               fma2(xj[kp], pack2(q.x, q.x), add2(cj[kp], pack2(q.w, q.w)))));
+                               fma2(xj[kp], pack2(q.x, q.x), pack2(q.w, q.w))));
               float a0, a1;
               unpack2(r2, a0, a1);
               mt[2 * kp] = fminf(mt[2 * kp], a0);
@@ -336,19 +344,21 @@ mch_collapse_kernel(const __grid_constant__ ColArgs a) {
           }
 #pragma unroll
           for (int k = 0; k < 4; ++k)
-            if (mt[k] <= cutf && (edge ? su[k] > u : su[k] >= 0)) refine(k, i0, i1);
+            if (mt[k] <= cutk[k] && (edge ? su[k] > u : su[k] >= 0)) refine(k, i0, i1);
         }
       } else {
-        double xj[4], yj[4], zj[4], cj[4];
+        double xj[4], yj[4], zj[4];
+        int cutk[4];
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
           const int q = q0 + 32 * k + lane;
           const bool live = q < nh;
           su[k] = live ? suof[q] : -1;
-          xj[k] = live ? (double)X[q] - (double)cen.x : 1.0e150;
-          yj[k] = live ? (double)Y[q] - (double)cen.y : 1.0e150;
-          zj[k] = live ? (double)Z[q] - (double)cen.z : 1.0e150;
-          cj[k] = fma(zj[k], zj[k], fma(yj[k], yj[k], xj[k] * xj[k]));
+          xj[k] = live ? (double)X[q] - (double)cen.x : 0.0;  // (dead columns: never candidates, su = -1)
+          yj[k] = live ? (double)Y[q] - (double)cen.y : 0.0;
+          zj[k] = live ? (double)Z[q] - (double)cen.z : 0.0;
+          // candidate threshold of this column, on the high word: r^2 - |p_j'|^2 + bias <= cut - |p_j'|^2 + bias
+          cutk[k] = __double2hiint((cut - fma(zj[k], zj[k], fma(yj[k], yj[k], xj[k] * xj[k]))) + bias);
         }
         for (; task < n_task; task += nwarps) {
           const bool edge = task >= n_rb;
@@ -362,22 +372,21 @@ mch_collapse_kernel(const __grid_constant__ ColArgs a) {
             const Row4<double> q = reinterpret_cast<const Row4<double>*>(Qh)[i];
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
-              const double r2 = fma(zj[k], q.z, fma(yj[k], q.y, fma(xj[k], q.x, cj[k] + q.w)));
-              mt[k] = min(mt[k], __double2hiint(r2));  // positive doubles order like their high words
-            }                                          // (a tiny r^2 rounded negative has a negative high word)
+              const double v = fma(zj[k], q.z, fma(yj[k], q.y, fma(xj[k], q.x, q.w)));  // = r^2 - |p_j'|^2 + bias > 0
+              mt[k] = min(mt[k], __double2hiint(v));  // positive doubles order like their high words
+            }
           }
 #pragma unroll
           for (int k = 0; k < 4; ++k)
-            if (mt[k] <= cuti && (edge ? su[k] > u : su[k] >= 0)) refine(k, i0, i1);
+            if (mt[k] <= cutk[k] && (edge ? su[k] > u : su[k] >= 0)) refine(k, i0, i1);
         }
       }
     }
     em = warp_min(em);
+    if (lane == 0) wsum[64 + warp] = (double)em;  // (slots [64, 96): last read before the barriers of the previous step)
     __syncthreads();
-    if (lane == 0) wsum[warp] = (double)em;
-    __syncthreads();
-    double v = wsum[0];
-    for (int w = 1; w < nwarps; ++w) v = fmin(v, wsum[w]);
+    double v = wsum[64];
+    for (int w = 1; w < nwarps; ++w) v = fmin(v, wsum[64 + w]);
     return v;  // exact minimum r^2 over the candidates (huge if there is none)
   };
   // "min distance < threshold"; when true, dmin is the exact minimum distance (dmin < 0: not computed)
