@@ -30,6 +30,10 @@
 #include "mch_device.cuh"
 #include "mch_optimize.cuh"
 
+#ifndef MCH_COL_RB
+#define MCH_COL_RB 64  // rows per task of the contact pass
+#endif
+
 namespace mch {
 
 struct ColArgs {
@@ -158,7 +162,7 @@ mch_collapse_kernel(const __grid_constant__ ColArgs a) {
   }
   __syncthreads();
 
-  constexpr int CT = 128, RB = 32;  // block = 4 column units x 32 rows
+  constexpr int CT = 128, RB = MCH_COL_RB;  // block = 4 column units x RB rows
   constexpr bool kFast = sizeof(T) == 4;
   // centre of the expanded encoding in fp64 mode: the start centroid of the contact-tested atoms
   double cen_x = 0.0, cen_y = 0.0, cen_z = 0.0;
@@ -407,27 +411,33 @@ mch_collapse_kernel(const __grid_constant__ ColArgs a) {
       if (lane == 0) { csum[3 * s] = sx; csum[3 * s + 1] = sy; csum[3 * s + 2] = sz; }
     }
     __syncthreads();
-    if (warp == 0) {
+    {
+      // Every warp forms the step vectors itself -- the same inputs, the same arithmetic, the same bits -- and
+      // writes them all (identical values from every warp: no warp has to wait for another one here).
       double tx = 0.0, ty = 0.0, tz = 0.0;
       for (int s = lane; s < S; s += 32) { tx += csum[3 * s]; ty += csum[3 * s + 1]; tz += csum[3 * s + 2]; }
       tx = warp_sum(tx) / N; ty = warp_sum(ty) / N; tz = warp_sum(tz) / N;
-      double big = 0.0;
-      for (int s = lane; s < S; s += 32) {
-        if (s >= Sm) { vec[3 * s] = 0.0; vec[3 * s + 1] = 0.0; vec[3 * s + 2] = 0.0; continue; }  // static group
+      auto centroid_vector = [&](int s, double& vx, double& vy, double& vz) {
         const double n = (double)((hoff[s + 1] - hoff[s]) + (loff[s + 1] - loff[s]));
-        const double vx = csum[3 * s] / n - tx, vy = csum[3 * s + 1] / n - ty, vz = csum[3 * s + 2] / n - tz;
-        vec[3 * s] = vx; vec[3 * s + 1] = vy; vec[3 * s + 2] = vz;
+        vx = csum[3 * s] / n - tx; vy = csum[3 * s + 1] / n - ty; vz = csum[3 * s + 2] / n - tz;
+      };
+      double big = 0.0;
+      for (int s = lane; s < Sm; s += 32) {
+        double vx, vy, vz;
+        centroid_vector(s, vx, vy, vz);
         big = fmax(big, sqrt(vx * vx + vy * vy + vz * vz));
       }
       big = warp_max(big);
-      __syncwarp();
-      for (int s = lane; s < Sm; s += 32) {
-        const double vx = vec[3 * s], vy = vec[3 * s + 1], vz = vec[3 * s + 2];
-        const double sc = a.scale_steps ? sqrt(vx * vx + vy * vy + vz * vz) / big : 1.0;
+      for (int s = lane; s < S; s += 32) {
+        double vx = 0.0, vy = 0.0, vz = 0.0, sc = 1.0;
+        if (s < Sm) {  // the static group (atoms in no subunit) keeps a zero vector
+          centroid_vector(s, vx, vy, vz);
+          if (a.scale_steps) sc = sqrt(vx * vx + vy * vy + vz * vz) / big;
+        }
         vec[3 * s] = (step * vx) * sc; vec[3 * s + 1] = (step * vy) * sc; vec[3 * s + 2] = (step * vz) * sc;
       }
+      __syncwarp();
     }
-    __syncthreads();
     for (int n = tid; n < N; n += nt) {
       const int s = suof[n];
       if (s >= Sm) continue;  // atoms in no subunit keep their positions bit for bit
