@@ -17,6 +17,9 @@ import sys
 PKG = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(PKG, "csrc")
 LIB = os.path.join(PKG, "libmchammer_b200.so")
+# check build (asserts + cluster race detector, mu = 3 / f64 position arrays only): used by tests/test_gpu_check_build.py
+CHECK_LIB = os.path.join(PKG, "libmchammer_b200_check.so")
+CHECK_DEFINES = ("MCH_QUICK", "MCH_RACECHECK")
 # bench-only measurement kernels (roofline denominators, sweep-only ceiling): their own library
 PROBES_DIR = os.path.join(os.path.dirname(PKG), "profiles", "probes")
 PROBES_SRC = os.path.join(PROBES_DIR, "mch_probes.cu")
@@ -42,10 +45,10 @@ def _nvcc() -> str:
     return exe
 
 
-def is_stale() -> bool:
-    if not os.path.exists(LIB):
+def is_stale(lib: str = LIB) -> bool:
+    if not os.path.exists(lib):
         return True
-    built = os.path.getmtime(LIB)
+    built = os.path.getmtime(lib)
     deps = [os.path.join(CSRC, s) for s in SOURCES + HEADERS] + [os.path.abspath(__file__)]
     return any(os.path.getmtime(d) > built for d in deps)
 
@@ -84,6 +87,14 @@ def build_library(force: bool = False, verbose: bool = False, defines=(), out: s
     return target
 
 
+def build_check_library(force: bool = False) -> str:
+    """libmchammer_b200_check.so: the same sources with -DMCH_RACECHECK (csrc/mch_device.cuh) -- device asserts
+    on the step descriptors and the race detector for the thread-block-cluster protocols."""
+    if not force and not is_stale(CHECK_LIB):
+        return CHECK_LIB
+    return build_library(force=True, defines=CHECK_DEFINES, out=CHECK_LIB)
+
+
 def build_probes(force: bool = False, defines=(), out: str | None = None) -> str:
     """profiles/probes/mch_probes.cu -> libmch_probes.so (bench-only; includes the product's device headers)."""
     target = out or PROBES_LIB
@@ -106,3 +117,4 @@ if __name__ == "__main__":
     print(path)
     if not outs:
         print(build_probes(force="--force" in sys.argv))
+        print(build_check_library(force="--force" in sys.argv))

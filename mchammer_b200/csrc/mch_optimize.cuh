@@ -41,6 +41,14 @@
 #include <cooperative_groups.h>
 #endif
 
+// slot of the double-buffered cluster exchange used at `step`; the negative control of the check build
+// (-DMCH_RACECHECK_BREAK=1) drops the double buffering, which the race detector must report
+#if defined(MCH_RACECHECK_BREAK) && MCH_RACECHECK_BREAK == 1
+#define MCH_RC_PARITY(step) 0
+#else
+#define MCH_RC_PARITY(step) ((step) & 1)
+#endif
+
 namespace mch {
 
 struct OptArgs {
@@ -91,7 +99,7 @@ struct Ctl {
 
 // Shared-memory carve-up, identical on host (size query) and device.
 struct OptLayout {
-  int x, y, z, colsum, colsum_stride, rows, E, erow, csum, invn, wsum, xsum, epart, suoff, bslot, bsu, ctl, total;
+  int x, y, z, colsum, colsum_stride, rows, E, erow, csum, invn, wsum, xsum, epart, suoff, bslot, bsu, ctl, rc, total;
 };
 
 MCH_HD int align_up(int v, int a) { return (v + a - 1) / a * a; }
@@ -123,6 +131,10 @@ MCH_HD OptLayout opt_layout(int N, int S, int B, int max_su, int tsize, int defe
   L.bsu = o; o += align_up(2 * B, 4) * 4;
   o = align_up(o, 16);
   L.ctl = o; o += (int)sizeof(Ctl);
+  L.rc = o;
+#ifdef MCH_RACECHECK  // shadows of the locations other CTAs of the cluster touch: xsum, epart, E (8 bytes each)
+  o += cluster > 1 ? (2 * kMaxCluster + 2 * kMaxCluster * S + S * S) * 8 : 0;
+#endif
   L.total = align_up(o, 16);
   return L;
 }
@@ -237,6 +249,14 @@ mch_optimize_kernel(const __grid_constant__ OptArgs a) {
   int* bslot = reinterpret_cast<int*>(smem + L.bslot);
   int* bsu = reinterpret_cast<int*>(smem + L.bsu);
   Ctl* ctl = reinterpret_cast<Ctl*>(smem + L.ctl);
+#ifdef MCH_RACECHECK
+  RcShadow* rc_xsum = reinterpret_cast<RcShadow*>(smem + L.rc);   // [2][kMaxCluster]
+  RcShadow* rc_epart = rc_xsum + 2 * kMaxCluster;                 // [2][kMaxCluster][S]
+  RcShadow* rc_E = rc_epart + 2 * kMaxCluster * S;                // [S][S]
+  unsigned rc_epoch = 1u;                                         // cluster barriers passed + 1
+  if (CL && G > 1)
+    for (int k = tid; k < 2 * kMaxCluster + 2 * kMaxCluster * S + S * S; k += nt) { rc_xsum[k].w = 0u; rc_xsum[k].r = 0u; }
+#endif
 
   const PairTerm<T, MUK> term(a.p.nonbond_mu, a.mu_int);
   const double scale = a.p.nonbond_epsilon * pow(a.p.nonbond_sigma, a.p.nonbond_mu);
@@ -260,7 +280,7 @@ mch_optimize_kernel(const __grid_constant__ OptArgs a) {
   for (int k = tid; k < S * S; k += nt) E[k] = 0.0;
   for (int k = tid; k < S; k += nt) invn[k] = 1.0 / (double)(suoff[k + 1] - suoff[k]);
   __syncthreads();
-  if (CL && G > 1) cooperative_groups::this_cluster().sync();  // every CTA's E is zeroed before any peer writes rows into it
+  if (CL && G > 1) { cooperative_groups::this_cluster().sync(); MCH_RC(++rc_epoch); }  // every CTA's E is zeroed before any peer writes rows into it
 
   // ---------------------------------------------------------------- control-warp state
   // (uniform across the 32 lanes of warp 0; other warps never read it)
@@ -421,8 +441,10 @@ mch_optimize_kernel(const __grid_constant__ OptArgs a) {
         v = warp_sum(v) * scale;
       }
       if (CL && G > 1) {
-        if (lane < G)
+        if (lane < G) {
+          MCH_RC(rc_write(cooperative_groups::this_cluster().map_shared_rank(rc_epart, lane) + (parity * kMaxCluster + rank) * S + t, rc_epoch, (unsigned)rank, "epart"));
           cooperative_groups::this_cluster().map_shared_rank(epart, lane)[(parity * kMaxCluster + rank) * S + t] = v;
+        }
       } else if (lane == 0 && t != row) {
         E[row * S + t] = v; E[t * S + row] = v;
       }
@@ -432,7 +454,10 @@ mch_optimize_kernel(const __grid_constant__ OptArgs a) {
     for (int t = lane; t < S; t += 32) {
       if (t == row) continue;
       double v = 0.0;
-      for (int r = 0; r < G; ++r) v += epart[(parity * kMaxCluster + r) * S + t];
+      for (int r = 0; r < G; ++r) {
+        MCH_RC(rc_read(rc_epart + (parity * kMaxCluster + r) * S + t, rc_epoch, (unsigned)rank, "epart"));
+        v += epart[(parity * kMaxCluster + r) * S + t];
+      }
       E[row * S + t] = v; E[t * S + row] = v;
     }
   };
@@ -472,7 +497,11 @@ mch_optimize_kernel(const __grid_constant__ OptArgs a) {
       vx = (cvx * ss) * rnd; vy = (cvy * ss) * rnd; vz = (cvz * ss) * rnd;
     }
     tvx = (T)vx; tvy = (T)vy; tvz = (T)vz;
+    MCH_CHECK(kb >= 0 && kb < B && ms >= 0 && ms < S, "bond / subunit index of the proposal");
+    MCH_CHECK(sa >= 0 && sa < N && sb >= 0 && sb < N, "slot of a bond end");
     const int n = fill_rows(ms, tvx, tvy, tvz);                    // :248-252  (pos - vector)
+    MCH_CHECK(n + 3 <= a.max_su + kRowSlack, "row buffer capacity (padded rows + prefetch overrun)");
+    MCH_CHECK(suoff[ms] >= 0 && suoff[ms] <= suoff[ms + 1] && suoff[ms + 1] <= N, "slot range of the moving subunit");
     if (lane == 0) {
       ctl->nrows = n; ctl->c0 = 0; ctl->g0 = suoff[ms]; ctl->g1 = suoff[ms + 1]; ctl->c1 = N; ctl->ms = ms;
       ctl->buf = kDefer ? buf : 0;
@@ -536,12 +565,25 @@ mch_optimize_kernel(const __grid_constant__ OptArgs a) {
       double* peer = cluster.map_shared_rank(E, r);
       for (int own = 0; own < S; ++own) {
         if (step0_owner(own) != rank) continue;
-        for (int t = own + 1 + tid; t < S; t += nt) { const double v = E[own * S + t]; peer[own * S + t] = v; peer[t * S + own] = v; }
+        for (int t = own + 1 + tid; t < S; t += nt) {
+          const double v = E[own * S + t];
+          MCH_RC(rc_write(cluster.map_shared_rank(rc_E, r) + own * S + t, rc_epoch, (unsigned)rank, "energy table"));
+          MCH_RC(rc_write(cluster.map_shared_rank(rc_E, r) + t * S + own, rc_epoch, (unsigned)rank, "energy table"));
+          peer[own * S + t] = v; peer[t * S + own] = v;
+        }
       }
     }
-    if (tid < G) cluster.map_shared_rank(xsum, tid)[rank] = ctl->U;  // parity-0 slots (the step loop starts with parity 1)
+    if (tid < G) {
+      MCH_RC(rc_write(cluster.map_shared_rank(rc_xsum, tid) + rank, rc_epoch, (unsigned)rank, "sweep totals"));
+      cluster.map_shared_rank(xsum, tid)[rank] = ctl->U;  // parity-0 slots (the step loop starts with parity 1)
+    }
     cluster.sync();
-    if (tid == 0) { double u = 0.0; for (int r = 0; r < G; ++r) u += xsum[r]; ctl->U = u; }
+    MCH_RC(++rc_epoch);
+    if (tid == 0) {
+      double u = 0.0;
+      for (int r = 0; r < G; ++r) { MCH_RC(rc_read(rc_xsum + r, rc_epoch, (unsigned)rank, "sweep totals")); u += xsum[r]; }
+      ctl->U = u;
+    }
     __syncthreads();
   }
   if (warp == 0) {
@@ -550,7 +592,11 @@ mch_optimize_kernel(const __grid_constant__ OptArgs a) {
     pair_count = (unsigned long long)N * (unsigned long long)(N - 1) / 2ULL;  // step 0: every pair once
     const double e_intra = ctl->U * scale;
     double cross = 0.0;
-    for (int k = lane; k < S * S; k += 32) { const int s = k / S, t = k - s * S; if (t > s) cross += E[k]; }
+    for (int k = lane; k < S * S; k += 32) {
+      const int s = k / S, t = k - s * S;
+      if (CL && G > 1 && t != s) { MCH_RC(rc_read(rc_E + k, rc_epoch, (unsigned)rank, "energy table")); }
+      if (t > s) cross += E[k];
+    }
     Unb = warp_sum(cross) + e_intra;
     refresh_erow();
     double longest;
@@ -629,15 +675,22 @@ mch_optimize_kernel(const __grid_constant__ OptArgs a) {
       if (warp == 0) {
         double mine = 0.0;
         for (int w = 0; w < nwarps; ++w) mine += wsum[w];
-        if (lane < G) cluster.map_shared_rank(xsum, lane)[(step & 1) * kMaxCluster + rank] = mine;
+        if (lane < G) {
+          MCH_RC(rc_write(cluster.map_shared_rank(rc_xsum, lane) + MCH_RC_PARITY(step) * kMaxCluster + rank, rc_epoch, (unsigned)rank, "sweep totals"));
+          cluster.map_shared_rank(xsum, lane)[MCH_RC_PARITY(step) * kMaxCluster + rank] = mine;
+        }
       }
       cluster.sync();
+      MCH_RC(++rc_epoch);
     }
     if (warp == 0) {
       unpark();
       double fresh = 0.0;
       if (CL && G > 1) {
-        for (int r = 0; r < G; ++r) fresh += xsum[(step & 1) * kMaxCluster + r];
+        for (int r = 0; r < G; ++r) {
+          MCH_RC(rc_read(rc_xsum + MCH_RC_PARITY(step) * kMaxCluster + r, rc_epoch, (unsigned)rank, "sweep totals"));
+          fresh += xsum[MCH_RC_PARITY(step) * kMaxCluster + r];
+        }
         if (d_accepted) {  // the row pushed under this step's sweep: needed from here on (erow below)
           install_partial_rows(d_ms, step & 1);
           refresh_erow();

@@ -76,7 +76,7 @@ struct WideCtl {
   double origin[3];
 };
 
-struct WideLayout { int x, y, z, qn, qo, r0, rw, bpos, bslot, bsu, xs, cs, wsum, ctl, total; };
+struct WideLayout { int x, y, z, qn, qo, r0, rw, bpos, bslot, bsu, xs, x0, cs, wsum, ctl, rc, total; };
 
 MCH_HD WideLayout wide_layout(int chunk, int B, int max_rows, int tsize) {
   WideLayout L;
@@ -97,9 +97,15 @@ MCH_HD WideLayout wide_layout(int chunk, int B, int max_rows, int tsize) {
   L.bsu = o; o += align_up(2 * B, 4) * 4;
   o = align_up(o, 16);
   L.xs = o; o += kWideMaxCluster * 2 * 8;
+  L.x0 = o; o += kWideMaxCluster * 8;  // step-0 totals: slots of their own (a fast CTA writes its step-1 totals into
+                                       // xs while a slow one may still be reading step 0's -- found by the check build)
   L.cs = o; o += kWideMaxCluster * 3 * 8;
   L.wsum = o; o += 3 * 32 * 8;
   L.ctl = o; o += (int)sizeof(WideCtl);
+  L.rc = o;
+#ifdef MCH_RACECHECK  // shadows: one per own slot (x, y, z together), per sweep-total entry, per coordinate-sum triple
+  o += (np + kWideMaxCluster * 2 + kWideMaxCluster + kWideMaxCluster) * 8;
+#endif
   L.total = align_up(o, 16);
   return L;
 }
@@ -135,9 +141,20 @@ mch_optimize_wide_kernel(const __grid_constant__ WideArgs a) {
   int* bslot = reinterpret_cast<int*>(smem + L.bslot);
   int* bsu = reinterpret_cast<int*>(smem + L.bsu);
   double* xs = reinterpret_cast<double*>(smem + L.xs);  // [G][2] per-CTA sweep totals (new, old)
+  double* x0 = reinterpret_cast<double*>(smem + L.x0);  // [G] per-CTA totals of step 0
   double* cs = reinterpret_cast<double*>(smem + L.cs);  // [G][3] per-CTA coordinate sums
   double* wsum = reinterpret_cast<double*>(smem + L.wsum);
   WideCtl* ctl = reinterpret_cast<WideCtl*>(smem + L.ctl);
+#ifdef MCH_RACECHECK
+  const int rc_np = align_up(chunk, 8);
+  RcShadow* rc_pos = reinterpret_cast<RcShadow*>(smem + L.rc);  // [chunk]
+  RcShadow* rc_xs = rc_pos + rc_np;                             // [G][2]
+  RcShadow* rc_cs = rc_xs + kWideMaxCluster * 2;                // [G]
+  RcShadow* rc_x0 = rc_cs + kWideMaxCluster;                    // [G]
+  unsigned rc_epoch = 1u;                                       // cluster barriers passed + 1
+  for (int k = tid; k < rc_np + kWideMaxCluster * 4; k += nt) { rc_pos[k].w = 0u; rc_pos[k].r = 0u; }
+  __syncthreads();
+#endif
 
   constexpr bool kFast = sizeof(T) == 4;
   constexpr bool kXF = kFast ? (MCH_XF != 0) : (MCH_XF64 != 0);
@@ -163,12 +180,15 @@ mch_optimize_wide_kernel(const __grid_constant__ WideArgs a) {
     block_sum3(sx, sy, sz);
     if (warp == 0 && lane < G) {
       double* peer = cluster.map_shared_rank(cs, lane);
+      MCH_RC(rc_write(cluster.map_shared_rank(rc_cs, lane) + rank, rc_epoch, (unsigned)rank, "coordinate sums"));
       peer[3 * rank] = sx; peer[3 * rank + 1] = sy; peer[3 * rank + 2] = sz;
     }
   };
   // positions of `count` atoms given by slot -> dst[3][rows_cap-strided], read from their owners (DSMEM)
   auto pull = [&](int slot, T& x, T& y, T& z) {
     const int q = slot / chunk, l = slot - q * chunk;
+    MCH_CHECK(slot >= 0 && slot < N && q < G, "slot of a pulled atom");
+    MCH_RC(rc_read(cluster.map_shared_rank(rc_pos, q) + l, rc_epoch, (unsigned)rank, "positions"));
     x = cluster.map_shared_rank(X, q)[l];
     y = cluster.map_shared_rank(Y, q)[l];
     z = cluster.map_shared_rank(Z, q)[l];
@@ -248,6 +268,7 @@ mch_optimize_wide_kernel(const __grid_constant__ WideArgs a) {
   }
   for (int l = tid; l < cnt; l += nt) {
     const long long src = in_base + 3LL * a.perm[lo + l];
+    MCH_RC(rc_write(rc_pos + l, rc_epoch, (unsigned)rank, "positions"));
     X[l] = (T)(load_io<Tio>(a.pos_in, src + 0) - origin[0]);
     Y[l] = (T)(load_io<Tio>(a.pos_in, src + 1) - origin[1]);
     Z[l] = (T)(load_io<Tio>(a.pos_in, src + 2) - origin[2]);
@@ -256,6 +277,7 @@ mch_optimize_wide_kernel(const __grid_constant__ WideArgs a) {
   if (tid == 0) { ctl->origin[0] = origin[0]; ctl->origin[1] = origin[1]; ctl->origin[2] = origin[2]; }
   __syncthreads();
   cluster.sync();  // every CTA's slots are loaded
+  MCH_RC(++rc_epoch);
   for (int k = tid; k < 2 * B; k += nt) {
     T x, y, z;
     pull(bslot[k], x, y, z);
@@ -309,9 +331,13 @@ mch_optimize_wide_kernel(const __grid_constant__ WideArgs a) {
   {
     double unused1 = 0.0, unused2 = 0.0;
     block_sum3(part0, unused1, unused2);
-    if (warp == 0 && lane < G) cluster.map_shared_rank(xs, lane)[2 * rank] = part0;
+    if (warp == 0 && lane < G) {
+      MCH_RC(rc_write(cluster.map_shared_rank(rc_x0, lane) + rank, rc_epoch, (unsigned)rank, "step-0 totals"));
+      cluster.map_shared_rank(x0, lane)[rank] = part0;
+    }
   }
   cluster.sync();  // step-0 totals and coordinate sums of every CTA are visible
+  MCH_RC(++rc_epoch);
 
   // ---------------------------------------------------------------- control state (warp 0, uniform)
   Pcg64 rng = pcg_load(a.rng + 6LL * c);
@@ -321,7 +347,7 @@ mch_optimize_wide_kernel(const __grid_constant__ WideArgs a) {
   unsigned long long pair_count = (unsigned long long)N * (unsigned long long)(N - 1) / 2ULL;
   if (warp == 0) {
     double tot = 0.0;
-    for (int r = 0; r < G; ++r) tot += xs[2 * r];
+    for (int r = 0; r < G; ++r) { MCH_RC(rc_read(rc_x0 + r, rc_epoch, (unsigned)rank, "step-0 totals")); tot += x0[r]; }
     Unb = tot * scale;
     double longest;
     U = Unb + bond_terms(-1, (T)0, (T)0, (T)0, longest);
@@ -355,6 +381,7 @@ mch_optimize_wide_kernel(const __grid_constant__ WideArgs a) {
     }
     __syncthreads();
     const int cur = ctl->ms, n = ctl->n, np = ctl->np, r_off = a.row_off[cur];
+    MCH_CHECK(cur >= 0 && cur < a.S && np + 3 <= rows_cap, "moving subunit / row buffer capacity");
     for (int i = tid; i < n; i += nt) {  // current positions of the moving atoms, from their owners
       T x, y, z;
       pull(a.row_slot[r_off + i], x, y, z);
@@ -371,7 +398,10 @@ mch_optimize_wide_kernel(const __grid_constant__ WideArgs a) {
       }
       sx = warp_sum(sx); sy = warp_sum(sy); sz = warp_sum(sz); sw = warp_sum(sw);
       double tx = 0.0, ty = 0.0, tz = 0.0;
-      for (int r = 0; r < G; ++r) { tx += cs[3 * r]; ty += cs[3 * r + 1]; tz += cs[3 * r + 2]; }
+      for (int r = 0; r < G; ++r) {
+        MCH_RC(rc_read(rc_cs + r, rc_epoch, (unsigned)rank, "coordinate sums"));
+        tx += cs[3 * r]; ty += cs[3 * r + 1]; tz += cs[3 * r + 2];
+      }
       const int sa = 2 * kb, sb = 2 * kb + 1;
       const double bvx = (double)bpos[sb] - (double)bpos[sa];        // :215-217 (P[b1] - P[b0])
       const double bvy = (double)bpos[bstride + sb] - (double)bpos[bstride + sa];
@@ -410,13 +440,20 @@ mch_optimize_wide_kernel(const __grid_constant__ WideArgs a) {
       block_sum3(p_new, p_old, unused);
       if (warp == 0 && lane < G) {
         double* peer = cluster.map_shared_rank(xs, lane);
+        MCH_RC(rc_write(cluster.map_shared_rank(rc_xs, lane) + 2 * rank, rc_epoch, (unsigned)rank, "sweep totals"));
+        MCH_RC(rc_write(cluster.map_shared_rank(rc_xs, lane) + 2 * rank + 1, rc_epoch, (unsigned)rank, "sweep totals"));
         peer[2 * rank] = p_new; peer[2 * rank + 1] = p_old;
       }
     }
     cluster.sync();  // barrier 1: every CTA's sweep totals are here
+    MCH_RC(++rc_epoch);
     if (warp == 0) {
       double fresh = 0.0, stale = 0.0;
-      for (int r = 0; r < G; ++r) { fresh += xs[2 * r]; stale += xs[2 * r + 1]; }
+      for (int r = 0; r < G; ++r) {
+        MCH_RC(rc_read(rc_xs + 2 * r, rc_epoch, (unsigned)rank, "sweep totals"));
+        MCH_RC(rc_read(rc_xs + 2 * r + 1, rc_epoch, (unsigned)rank, "sweep totals"));
+        fresh += xs[2 * r]; stale += xs[2 * r + 1];
+      }
       const double Unb_new = Unb + (fresh - stale) * scale;
       const double U_new = Unb_new + Ub_trial;
       bool ok;
@@ -459,6 +496,7 @@ mch_optimize_wide_kernel(const __grid_constant__ WideArgs a) {
           for (int l = b + tid; l < e; l += nt) {
             T x = X[l] - tvx, y = Y[l] - tvy, z = Z[l] - tvz;
             if (!ok) { x = x - (-tvx); y = y - (-tvy); z = z - (-tvz); }
+            MCH_RC(rc_write(rc_pos + l, rc_epoch, (unsigned)rank, "positions"));
             X[l] = x; Y[l] = y; Z[l] = z;
           }
         }
@@ -469,7 +507,10 @@ mch_optimize_wide_kernel(const __grid_constant__ WideArgs a) {
       }
       if (a.traj) { __syncthreads(); write_frame(step); }
     }
+#if !(defined(MCH_RACECHECK_BREAK) && MCH_RACECHECK_BREAK == 2)  // negative control of the check build: no barrier 2
     cluster.sync();  // barrier 2: positions and coordinate sums are final before the next pull
+    MCH_RC(++rc_epoch);
+#endif
   }
 
   // ---------------------------------------------------------------- epilogue
@@ -491,11 +532,16 @@ template <typename T, typename Tio>
 int launch_wide_io(int mk, const WideArgs& a, int threads, int smem, cudaStream_t s) {
   const int blocks = a.C * a.G;
   const char* what = "mch_optimize_batch (split-state kernel)";
+#ifdef MCH_QUICK
+  if (mk != MU_3) return fail(-3, "MCH_QUICK build: mu = 3 only");
+  return launch_clustered_wide(mch_optimize_wide_kernel<T, Tio, MU_3>, a, blocks, threads, smem, a.G, s, what);
+#else
   switch (mk) {
     case MU_3: return launch_clustered_wide(mch_optimize_wide_kernel<T, Tio, MU_3>, a, blocks, threads, smem, a.G, s, what);
     case MU_INT: return launch_clustered_wide(mch_optimize_wide_kernel<T, Tio, MU_INT>, a, blocks, threads, smem, a.G, s, what);
     default: return launch_clustered_wide(mch_optimize_wide_kernel<T, Tio, MU_REAL>, a, blocks, threads, smem, a.G, s, what);
   }
+#endif
 }
 
 #endif  // __CUDACC__

@@ -4,7 +4,12 @@
 
 namespace mch {
 int launch_wide_f32(bool io_f64, int mk, const WideArgs& a, int threads, int smem, cudaStream_t s) {
+#ifdef MCH_QUICK
+  if (!io_f64) return fail(-3, "MCH_QUICK build: f64 position arrays only");
+  return launch_wide_io<float, double>(mk, a, threads, smem, s);
+#else
   return io_f64 ? launch_wide_io<float, double>(mk, a, threads, smem, s)
                 : launch_wide_io<float, float>(mk, a, threads, smem, s);
+#endif
 }
 }  // namespace mch
