@@ -16,6 +16,10 @@
 #include "mch_device.cuh"
 #include "mch_optimize.cuh"  // align_up, load_io
 
+#ifndef MCH_POT_X2
+#define MCH_POT_X2 1  // fp32: the cross sweeps on the packed plain-form tile
+#endif
+
 namespace mch {
 
 struct PotArgs {
@@ -95,8 +99,8 @@ mch_potential_kernel(const __grid_constant__ PotArgs a) {
   // eps (|p_i'| + |p_j'|)^2 / r^2 is harmless in fp64 (~1e-13) but not in fp32 (~1e-4 on the closest pairs).
   constexpr bool kFast = sizeof(T) == 4;
   constexpr bool kXF = !kFast && (MCH_XF64 != 0);
-  constexpr bool kX2 = false;
-  constexpr int kRot3 = 0;
+  constexpr bool kX2 = kFast && (MCH_F32X2 != 0) && (MCH_POT_X2 != 0);  // packed instructions, plain form (sweep_tile_x2<PLAIN>)
+  constexpr int kRot3 = kX2 ? 2 : 0;
   double mine = 0.0;
   Row4<T>* Qw = Q + warp * (POT_ROWB + 2 + kRowSlack);  // this warp's row buffer
   const int nblocks = (N + POT_ROWB - 1) / POT_ROWB;
