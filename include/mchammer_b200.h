@@ -64,7 +64,7 @@ typedef struct mch_optimize_desc {
   int32_t compute_dtype;      /* MCH_F64: parity mode; MCH_F32: fast mode                */
   int32_t inexact_undo;       /* 1: on reject redo (p - v) + v like optimizer.py:273-277 */
   int32_t threads_per_chain;  /* 0 = auto; else multiple of 32, <= 1024 (fp32) / 512 (fp64) */
-  int32_t cluster_size;       /* CTAs (SMs) per chain: 0 = auto, 1 = one CTA, 2 / 4 / 8 = thread-block cluster */
+  int32_t cluster_size;       /* CTAs (SMs) per chain: 0 = auto, 1 = one CTA, 2 / 4 / 8 / 16 = thread-block cluster */
   int32_t resident_chains_hint; /* 0, or the number of chains of the whole batch when the caller cuts one batch
                                  into several launches that run concurrently (pipelined slices): block size,
                                  cluster and occupancy choices are then made for the batch, not per slice */

@@ -271,15 +271,17 @@ int mch_optimize_batch(const mch_optimize_desc* d, void* stream) {
   // Thread-block cluster per chain: worth it when the GPU would otherwise be mostly idle and the
   // sweep is long enough to pay for one cluster barrier per step (big molecule, few chains).
   int cluster = d->cluster_size;
-  if (cluster != 0 && cluster != 1 && cluster != 2 && cluster != 4 && cluster != 8)
-    return fail(MCH_ERR_INVALID, "mch_optimize_batch: cluster_size must be 0 (auto), 1, 2, 4 or 8, got %d", cluster);
+  if (cluster != 0 && cluster != 1 && cluster != 2 && cluster != 4 && cluster != 8 && cluster != 16)
+    return fail(MCH_ERR_INVALID, "mch_optimize_batch: cluster_size must be 0 (auto), 1, 2, 4, 8 or 16, got %d", cluster);
   // an explicit block size outside what a chain on a cluster takes keeps the chain on one CTA
   const bool threads_fit_cluster = d->threads_per_chain == 0 || (d->threads_per_chain >= 64 && d->threads_per_chain <= 512);
   if (cluster == 0) {
     cluster = 1;
     if (d->n_atoms >= 768 && d->num_steps > 1 && threads_fit_cluster) {  // measured: profiles/r01_cluster_chain.txt
-      for (int g = d->n_atoms >= 2048 ? 8 : 4; g >= 2; g /= 2)
-        if (batch * g <= sms) {
+      // 16 CTAs (the non-portable cluster size; one such cluster per GPC) from 4096 atoms: the sweep of one
+      // chain is bound by the arithmetic pipes of the SMs it runs on (profiles/r02_cluster_chain.txt)
+      for (int g = d->n_atoms >= 4096 ? 16 : (d->n_atoms >= 2048 ? 8 : 4); g >= 2; g /= 2)
+        if (batch * g <= sms && (g < 16 || batch <= 8)) {
           int defer_unused;
           if (plan_chain_smem(d->n_atoms, d->n_subunits, d->n_bonds, d->max_subunit_atoms, d->compute_dtype,
                               &defer_unused, g) <= kMaxSmem) cluster = g;

@@ -85,12 +85,12 @@ int launch_optimize_cluster(int mk, const OptArgs& a, int threads, int smem, cud
   const int blocks = a.C * a.cluster;
 #ifdef MCH_QUICK
   if (mk != MU_3) return fail(-3, "MCH_QUICK build: mu = 3 only");
-  return launch_clustered(mch_optimize_kernel<T, Tio, MU_3, NT, true>, a, blocks, threads, smem, a.cluster, s, "mch_optimize_batch");
+  return launch_clustered_wide(mch_optimize_kernel<T, Tio, MU_3, NT, true>, a, blocks, threads, smem, a.cluster, s, "mch_optimize_batch");
 #else
   switch (mk) {
-    case MU_3: return launch_clustered(mch_optimize_kernel<T, Tio, MU_3, NT, true>, a, blocks, threads, smem, a.cluster, s, "mch_optimize_batch");
-    case MU_INT: return launch_clustered(mch_optimize_kernel<T, Tio, MU_INT, NT, true>, a, blocks, threads, smem, a.cluster, s, "mch_optimize_batch");
-    default: return launch_clustered(mch_optimize_kernel<T, Tio, MU_REAL, NT, true>, a, blocks, threads, smem, a.cluster, s, "mch_optimize_batch");
+    case MU_3: return launch_clustered_wide(mch_optimize_kernel<T, Tio, MU_3, NT, true>, a, blocks, threads, smem, a.cluster, s, "mch_optimize_batch");
+    case MU_INT: return launch_clustered_wide(mch_optimize_kernel<T, Tio, MU_INT, NT, true>, a, blocks, threads, smem, a.cluster, s, "mch_optimize_batch");
+    default: return launch_clustered_wide(mch_optimize_kernel<T, Tio, MU_REAL, NT, true>, a, blocks, threads, smem, a.cluster, s, "mch_optimize_batch");
   }
 #endif
 }

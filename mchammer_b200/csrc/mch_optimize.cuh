@@ -104,7 +104,7 @@ struct OptLayout {
 
 MCH_HD int align_up(int v, int a) { return (v + a - 1) / a * a; }
 
-constexpr int kMaxCluster = 8;
+constexpr int kMaxCluster = 16;  // 16 = the non-portable cluster size (opted in at launch)
 
 MCH_HD OptLayout opt_layout(int N, int S, int B, int max_su, int tsize, int defer, int cluster = 1) {
   OptLayout L;
@@ -114,7 +114,9 @@ MCH_HD OptLayout opt_layout(int N, int S, int B, int max_su, int tsize, int defe
   L.y = o; o += np * tsize;
   L.z = o; o += np * tsize;
   L.colsum = o; L.colsum_stride = np * (tsize < 4 ? 4 : tsize);
-  o += (defer ? 2 : 1) * L.colsum_stride;  // double buffered when control work is deferred
+  // double buffered when control work is deferred -- except on a cluster: there the column sums of an accepted
+  // sweep are consumed by all warps (coop_row) before the next sweep starts, so one buffer serves
+  o += (defer && cluster <= 1 ? 2 : 1) * L.colsum_stride;
   o = align_up(o, 32);
   L.rows = o; o += (max_su + kRowSlack) * row_bytes(tsize);  // + far-away padding row + prefetch overrun
   o = align_up(o, 16);
@@ -293,6 +295,7 @@ mch_optimize_kernel(const __grid_constant__ OptArgs a) {
   constexpr bool kX2 = kFast && kXF && (MCH_F32X2 != 0);  // packed-instruction tile
   constexpr int kRot3 = !(kX2 && (MCH_X2_ROT3 != 0)) ? 0 : (NTMAX <= 512 ? 2 : 1);  // 2: deep row prefetch (128 registers)
   const bool kDefer = a.defer != 0;  // host policy: off when the second buffer would cost a resident chain
+  const bool kTwoBuf = kDefer && !(CL && G > 1);  // two column-sum buffers (see opt_layout)
   // re-sum an accepted move's row of E with all warps (coop_row) where warp 0 alone would take long
   const bool kCoop = nwarps > 1 && ((CL && G > 1) || !kDefer || a.max_su > REGROUP_SMALL);
   Pcg64 rng;  // loaded after step 0 (nothing of the control state is live across the step-0 sweeps)
@@ -504,7 +507,7 @@ mch_optimize_kernel(const __grid_constant__ OptArgs a) {
     MCH_CHECK(suoff[ms] >= 0 && suoff[ms] <= suoff[ms + 1] && suoff[ms + 1] <= N, "slot range of the moving subunit");
     if (lane == 0) {
       ctl->nrows = n; ctl->c0 = 0; ctl->g0 = suoff[ms]; ctl->g1 = suoff[ms + 1]; ctl->c1 = N; ctl->ms = ms;
-      ctl->buf = kDefer ? buf : 0;
+      ctl->buf = kTwoBuf ? buf : 0;
     }
   };
   // exp(x) > r for x <= 0, r in [0, 1): decided by a fast fp32 exponential whenever it is
@@ -625,7 +628,7 @@ mch_optimize_kernel(const __grid_constant__ OptArgs a) {
       }
     }
     if (kCoop && ctl->d_accepted != 0) {  // uniform over the CTA: published by warp 0 before barrier A
-      coop_row(colsum + (kDefer ? ((step - 1) & 1) : 0) * colsum_stride, ctl->d_ms, step & 1);
+      coop_row(colsum + (kTwoBuf ? ((step - 1) & 1) : 0) * colsum_stride, ctl->d_ms, step & 1);
       __syncthreads();
     }
     if (warp == 0) {
@@ -735,7 +738,7 @@ mch_optimize_kernel(const __grid_constant__ OptArgs a) {
       }
       __syncwarp();
       info = kb | ((ok ? 1 : 0) << 16) | (kind << 17) | (ms << 18);
-      d_accepted = ok; d_ms = ms; d_buf = kDefer ? (step & 1) : 0; d_step = step;
+      d_accepted = ok; d_ms = ms; d_buf = kTwoBuf ? (step & 1) : 0; d_step = step;
       if (kCoop && lane == 0) { ctl->d_accepted = ok ? 1 : 0; ctl->d_ms = ms; }  // for coop_row after barrier A
       if (!kDefer) {
         if (!kCoop) {

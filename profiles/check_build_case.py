@@ -34,7 +34,7 @@ def run(tag, pos, bonds, subunits, steps, precision, cluster, chains, split, thr
 mol, bonds, subunits = synthetic.cube_cage()
 pos = mol.get_position_matrix()
 for precision in ("fp64", "fp32"):
-    for g in (2, 4, 8):  # the replicated-state cluster of the one-CTA kernel (csrc/mch_optimize.cuh, CL = true)
+    for g in (2, 4, 8, 16):  # the replicated-state cluster of the one-CTA kernel (csrc/mch_optimize.cuh, CL = true)
         run(f"replicated {precision} G={g}", pos, bonds, subunits, 80, precision, g, 3, False)
     for g in (1, 2, 4, 8, 16):  # the split-state kernel (csrc/mch_wide.cuh)
         if g == 16 and precision == "fp64":

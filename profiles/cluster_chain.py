@@ -20,7 +20,7 @@ def run(name, mol, bonds, su, steps, precision, chains=1):
     pos = torch.from_numpy(mol.get_position_matrix()).cuda()
     words = rngstate.seed_states(list(range(1000, 1000 + chains)))
     base = None
-    for cluster in (1, 2, 4, 8):
+    for cluster in (1, 2, 4, 8, 16):
         best, out = 1e9, None
         try:
             for _ in range(4):

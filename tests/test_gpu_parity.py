@@ -459,10 +459,10 @@ def test_large_cage_against_oracle_both_precisions():
     assert np.allclose(fast.positions[0], want.final_positions, rtol=0, atol=1e-3)
 
 
-@pytest.mark.parametrize("cluster", [2, 4, 8])
+@pytest.mark.parametrize("cluster", [2, 4, 8, 16])
 @pytest.mark.parametrize("precision", ["fp64", "fp32"])
 def test_chain_on_a_thread_block_cluster(cluster, precision):
-    # one chain spread over 2 / 4 / 8 CTAs (every CTA runs the control section redundantly, the sweep's
+    # one chain spread over 2 / 4 / 8 / 16 CTAs (16 = the non-portable cluster size) (every CTA runs the control section redundantly, the sweep's
     # columns are split, totals and new energy-table rows travel through distributed shared memory):
     # same decisions and, up to the grouping of the sums, the same numbers as the one-CTA chain;
     # fp64 also against the oracle
