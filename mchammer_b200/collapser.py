@@ -111,9 +111,9 @@ class Collapser:
         torch = native.require_cuda()
         dev = self._torch_device()
         elements = [a.get_element_string() for a in mol.get_atoms()]
-        topo = lower_topology(mol.get_num_atoms(), bond_pair_ids, subunits, elements=elements,
-                              require_bond_subunits=False)
-        dtopo = engine.upload_topology(topo, dev.index)
+        dtopo = engine.cached_topology(mol.get_num_atoms(), bond_pair_ids, subunits, dev.index, elements=elements,
+                                       require_bond_subunits=False)
+        topo = dtopo.host
         pos = torch.from_numpy(np.ascontiguousarray(positions)).to(dev)
         out = engine.collapse_on_device(
             dtopo, pos, n_mol, self._step_size, self._distance_threshold, self._scale_steps,

@@ -63,22 +63,66 @@ class DeviceTopology:
 
 
 def upload_topology(topo: LoweredTopology, device=None) -> DeviceTopology:
+    """All topology arrays in ONE host buffer and one host-to-device copy (they are tiny: a copy each used to
+    cost more than the arrays' bytes); the fields are 16-byte aligned views of that buffer."""
     torch = native.require_cuda()
     dev = torch.device("cuda", torch.cuda.current_device() if device is None else device)
-
-    def put(a):
-        return torch.from_numpy(np.ascontiguousarray(a, dtype=np.int32)).to(dev)
-
     slot_of = np.empty(topo.n_atoms, dtype=np.int64)
     slot_of[topo.perm] = np.arange(topo.n_atoms)
-    return DeviceTopology(
-        host=topo, device=dev, perm=put(topo.perm), su_offsets=put(topo.su_offsets),
-        bonds=put(topo.bonds.reshape(-1)), bond_su=put(topo.bond_su.reshape(-1)),
-        n_heavy=put(topo.n_heavy),
-        bond_slots=put(slot_of[topo.bonds.reshape(-1)]) if topo.n_bonds else put(np.zeros(0)),
-        row_offsets=put(topo.row_offsets), row_slots=put(topo.row_slots), row_weights=put(topo.row_weights),
-        run_offsets=put(topo.run_offsets), runs=put(topo.runs.reshape(-1)),
+    parts = dict(
+        perm=topo.perm, su_offsets=topo.su_offsets, bonds=topo.bonds.reshape(-1), bond_su=topo.bond_su.reshape(-1),
+        n_heavy=topo.n_heavy,
+        bond_slots=slot_of[topo.bonds.reshape(-1)] if topo.n_bonds else np.zeros(0, dtype=np.int32),
+        row_offsets=topo.row_offsets, row_slots=topo.row_slots, row_weights=topo.row_weights,
+        run_offsets=topo.run_offsets, runs=topo.runs.reshape(-1),
     )
+    offsets, total = {}, 0
+    for name, a in parts.items():
+        offsets[name] = total
+        total += (int(np.size(a)) + 3) // 4 * 4
+    packed = np.zeros(max(total, 4), dtype=np.int32)
+    for name, a in parts.items():
+        n = int(np.size(a))
+        packed[offsets[name]:offsets[name] + n] = np.asarray(a).reshape(-1)
+    buf = torch.from_numpy(packed).to(dev)
+    views = {name: buf[offsets[name]:offsets[name] + int(np.size(a))] for name, a in parts.items()}
+    return DeviceTopology(host=topo, device=dev, **views)
+
+
+_TOPOLOGY_CACHE: "dict[tuple, DeviceTopology]" = {}
+_TOPOLOGY_CACHE_SIZE = 16
+
+
+def cached_topology(n_atoms: int, bond_pair_ids, subunits, device_index: int, elements=None,
+                    require_bond_subunits: bool = True, allow_overlap: bool = False) -> DeviceTopology:
+    """``upload_topology(lower_topology(...))`` with a small LRU cache: a user who optimises many conformers of
+    one molecule (same bonds, same subunits) pays the lowering and the upload once.  The key holds the exact
+    inputs (bond pairs in the caller's order, subunit keys and member lists in dict order), so a hit returns
+    what a fresh lowering would."""
+    from .lowering import lower_topology
+
+    try:
+        bonds_key = np.asarray(bond_pair_ids, dtype=np.int64).tobytes()
+        keys = tuple(subunits)
+        lens = tuple(len(subunits[k]) for k in keys)
+        members = np.fromiter((a for k in keys for a in subunits[k]), dtype=np.int64, count=sum(lens)).tobytes()
+        key = (int(n_atoms), int(device_index), bool(require_bond_subunits), bool(allow_overlap),
+               None if elements is None else tuple(elements), bonds_key, keys, lens, members)
+        hash(key)
+    except (TypeError, ValueError):  # unhashable subunit keys, ragged bond lists, ...: let the lowering report it
+        key = None
+    if key is not None and key in _TOPOLOGY_CACHE:
+        dtopo = _TOPOLOGY_CACHE.pop(key)
+        _TOPOLOGY_CACHE[key] = dtopo  # most recently used last
+        return dtopo
+    topo = lower_topology(n_atoms, bond_pair_ids, subunits, elements=elements,
+                          require_bond_subunits=require_bond_subunits, allow_overlap=allow_overlap)
+    dtopo = upload_topology(topo, device_index)
+    if key is not None:
+        _TOPOLOGY_CACHE[key] = dtopo
+        while len(_TOPOLOGY_CACHE) > _TOPOLOGY_CACHE_SIZE:
+            _TOPOLOGY_CACHE.pop(next(iter(_TOPOLOGY_CACHE)))
+    return dtopo
 
 
 @dataclass

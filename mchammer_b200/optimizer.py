@@ -139,11 +139,11 @@ class Optimizer:
     def _run_single(self, mol: Molecule, bond_pair_ids, subunits, want_trace: bool):
         torch = native.require_cuda()
         dev = self._torch_device()
-        topo = lower_topology(
-            mol.get_num_atoms(), bond_pair_ids, subunits,
+        dtopo = engine.cached_topology(
+            mol.get_num_atoms(), bond_pair_ids, subunits, dev.index,
             require_bond_subunits=self._num_steps > 1, allow_overlap=True,
         )
-        dtopo = engine.upload_topology(topo, dev.index)
+        topo = dtopo.host
         pos = torch.from_numpy(mol.get_position_matrix()).to(dev)
         words = rngstate.words_from_bit_generator(self._generator.bit_generator)
         rng_dev = engine.rng_words_to_device(words[None, :], dev)

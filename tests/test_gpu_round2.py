@@ -16,6 +16,7 @@ import pytest
 
 import mchammer_b200 as mch
 from mchammer_b200 import stk_helpers, synthetic
+from mchammer_b200.lowering import lower_topology
 from oracle import mch_oracle as orc
 from tests.conftest import golden_bonds, golden_subunits, load_golden
 from tests.test_gpu_parity import RTOL32, RTOL64, golden_molecule, rel_close
@@ -341,3 +342,35 @@ def test_stk_optimize_batch_against_oracle():
         assert rel_close(record["system_potential"], want.system_potential[-1], RTOL64)
         assert record["n_accepted"] == int((want.passed == 1).sum())
         assert record["passed"] == bool(want.passed[-1])
+
+
+def test_topology_cache_returns_what_a_fresh_lowering_would():
+    # the drop-in calls keep the lowered + uploaded topology of recent (bonds, subunits) inputs; the key is the
+    # exact input (order of the bond pairs, dict order and member order of the subunits)
+    from mchammer_b200 import engine
+
+    mol, long_bonds, subunits = synthetic.cube_cage(atoms_per_subunit=6, seed=3, spread=5.0)
+    n = mol.get_num_atoms()
+    engine._TOPOLOGY_CACHE.clear()
+    a = engine.cached_topology(n, long_bonds, subunits, 0, allow_overlap=True)
+    b = engine.cached_topology(n, [tuple(p) for p in long_bonds], {k: list(v) for k, v in subunits.items()}, 0,
+                               allow_overlap=True)
+    assert a is b and len(engine._TOPOLOGY_CACHE) == 1
+    flipped = [tuple(long_bonds[0][::-1])] + [tuple(p) for p in long_bonds[1:]]  # the sign of one bond vector
+    c = engine.cached_topology(n, flipped, subunits, 0, allow_overlap=True)
+    assert c is not a and not np.array_equal(c.host.bonds, a.host.bonds)
+    reordered = dict(reversed(list(subunits.items())))  # dict order decides which subunit owns a bond end
+    d = engine.cached_topology(n, long_bonds, reordered, 0, allow_overlap=True)
+    assert d is not a
+    fresh = lower_topology(n, long_bonds, subunits, allow_overlap=True)
+    assert np.array_equal(a.perm.cpu().numpy(), fresh.perm) and np.array_equal(a.su_offsets.cpu().numpy(), fresh.su_offsets)
+    assert np.array_equal(a.row_slots.cpu().numpy(), fresh.row_slots) and np.array_equal(a.runs.cpu().numpy(), fresh.runs.reshape(-1))
+    # same chain with a warm and with a cold cache
+    opt1 = mch.Optimizer(0.25, 1.2, 40, random_seed=5)
+    warm = opt1.get_result(mol, long_bonds, subunits)[1]
+    engine._TOPOLOGY_CACHE.clear()
+    cold = mch.Optimizer(0.25, 1.2, 40, random_seed=5).get_result(mol, long_bonds, subunits)[1]
+    assert warm.system_potential == cold.system_potential and np.array_equal(warm.position_matrix, cold.position_matrix)
+    for k in range(engine._TOPOLOGY_CACHE_SIZE + 3):  # bounded
+        engine.cached_topology(n, long_bonds[: 1 + k % len(long_bonds)] * (1 + k // len(long_bonds)), subunits, 0, allow_overlap=True)
+    assert len(engine._TOPOLOGY_CACHE) <= engine._TOPOLOGY_CACHE_SIZE
