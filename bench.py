@@ -316,6 +316,8 @@ def secondary_lines(torch, dist, device, world: int, rank: int, flush, main_valu
       fp64         parity mode on the headline workload (cube1000, 4096 chains/GPU, num_steps 500)
       m12l24_fp32  BASELINE configs[4]: 65,536 chains of the 5004-atom cage in all, 65,536 / world per GPU (strong)
       strong_4096  the FIXED 4096-chain cube1000 batch split over the ranks (strong scaling)
+      collapser_fp64 / collapser_fp32, potential_fp64 / potential_fp32   the Collapser loop and compute_potential
+                   on 4096 molecules of 1000 atoms per GPU (rank 0's numbers)
     """
     import mchammer_b200 as mch
     from mchammer_b200 import engine, native, rngstate, synthetic
@@ -373,6 +375,63 @@ def secondary_lines(torch, dist, device, world: int, rank: int, flush, main_valu
         "roofline": {"bound": "fp32_pipe", "achieved": ach, "peak": peak32, "unit": "TFLOP/s",
                      "frac": ach / peak32 if peak32 else None},
     }
+    # --- the sibling kernels of the path (rank 0's GPU only; every rank runs them so that the ranks stay in step)
+    import numpy as np
+
+    def best_of(fn, reps=3):
+        fn()
+        best = None
+        for _ in range(reps):
+            flush.zero_()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(); fn(); e1.record(); e1.synchronize()
+            t = e0.elapsed_time(e1) * 1e-3
+            best = t if best is None else min(best, t)
+        return best
+
+    # Collapser loop (reference collapser.py:200-340): 4096 cages of 1000 atoms (30 % hydrogens), ~14 steps each
+    cmol, cbonds, csub = synthetic.cube_cage(h_fraction=0.3)
+    ctopo = lower_topology(cmol.get_num_atoms(), cbonds, csub, elements=[a.get_element_string() for a in cmol.get_atoms()],
+                           require_bond_subunits=False)
+    cdtopo = engine.upload_topology(ctopo, device.index)
+    nh = ctopo.n_heavy.astype(np.int64)
+    pairs_per_test = int((nh.sum() ** 2 - (nh ** 2).sum()) // 2)
+    crng = np.random.default_rng(5)
+    cbase = cmol.get_position_matrix()
+    n_cages = 4096
+    cpos = torch.from_numpy(np.stack([cbase * (1.0 + 0.004 * crng.random()) for _ in range(n_cages)])).to(device)
+    for precision, peak in (("fp64", peak64), ("fp32", peak32)):
+        res = engine.collapse_on_device(cdtopo, cpos, n_cages, 0.02, 1.5, True, precision)
+        steps_run = int(res.steps_run.sum().item())
+        sec = best_of(lambda: engine.collapse_on_device(cdtopo, cpos, n_cages, 0.02, 1.5, True, precision))
+        rate = (steps_run + n_cages) * pairs_per_test / sec  # one contact test before the first step, one after each
+        out["collapser_" + precision] = {
+            "workload": f"Collapser(step_size=0.02, distance_threshold=1.5, scale_steps=True): {n_cages} cages x 1000 atoms "
+                        f"({int(nh.sum())} non-H), {steps_run / n_cages:.1f} steps each, device resident",
+            "value": steps_run / sec, "unit": "molecule-steps/s", "ms_per_launch": 1e3 * sec,
+            "contact_pairs_per_s": rate,
+            "roofline": {"bound": precision + "_pipe", "achieved": 9.0 * rate / 1e12, "peak": peak, "unit": "TFLOP/s",
+                         "frac": 9.0 * rate / 1e12 / peak if peak else None,
+                         "note": "9 flops per contact pair credited (the plain form: 3 sub + mul + 2 fma + compare/select); "
+                                 "the fast form executes 6 flops + 1 min"},
+        }
+    del cpos
+    # compute_potential for a batch (reference optimizer.py:114-142): 4096 molecules x 1000 atoms, all pairs
+    pmol, pbonds, _ = build_workload("cube1000")
+    n_p = pmol.get_num_atoms()
+    ppos = torch.from_numpy(np.stack([pmol.get_position_matrix()] * 4096)).to(device)
+    pb = torch.tensor(np.asarray(pbonds, dtype=np.int32).reshape(-1), dtype=torch.int32, device=device)
+    popt = mch.Optimizer(step_size=0.25, target_bond_length=1.2, num_steps=2)
+    for precision, peak in (("fp64", peak64), ("fp32", peak32)):
+        sec = best_of(lambda: engine.potential_on_device(ppos, pb, len(pbonds), popt._params(), precision))
+        rate = 4096 * (n_p * (n_p - 1) // 2) / sec
+        out["potential_" + precision] = {
+            "workload": f"compute_potential: 4096 molecules x {n_p} atoms, all pairs + {len(pbonds)} bond terms, device resident",
+            "value": 4096 / sec, "unit": "molecules/s", "ms_per_launch": 1e3 * sec, "pair_evals_per_s": rate,
+            "roofline": {"bound": precision + "_pipe", "achieved": FLOPS_PER_PAIR * rate / 1e12, "peak": peak,
+                         "unit": "TFLOP/s", "frac": FLOPS_PER_PAIR * rate / 1e12 / peak if peak else None},
+        }
+    del ppos
     # --- strong scaling: the fixed 4096-chain batch over all ranks
     total = 4096
     num_steps = WORKLOADS["cube1000"]["num_steps"]
