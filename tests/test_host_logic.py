@@ -189,6 +189,12 @@ def test_library_exports_every_declared_symbol():
     out = subprocess.run(["nm", "-D", "--defined-only", native.LIB_PATH], capture_output=True, text=True).stdout
     for name in declared:
         assert re.search(rf"\bT {name}\b", out), name
+    # the check build (device asserts + cluster race detector) has the same C ABI
+    check = os.path.join(os.path.dirname(native.LIB_PATH), "libmchammer_b200_check.so")
+    if os.path.exists(check):
+        out = subprocess.run(["nm", "-D", "--defined-only", check], capture_output=True, text=True).stdout
+        for name in declared:
+            assert re.search(rf"\bT {name}\b", out), name
 
 
 def test_ctypes_structs_match_header_layout(tmp_path):
