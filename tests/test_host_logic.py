@@ -5,6 +5,7 @@ the product path refuses to run without CUDA instead of falling back to a CPU pa
 from __future__ import annotations
 
 import ctypes as CT
+import json
 import os
 import re
 import subprocess
@@ -418,3 +419,21 @@ def test_two_rank_gloo_sharding_and_gather(tmp_path):
     )
     assert proc.returncode == 0, proc.stderr[-2000:]
     assert "GATHER_OK" in proc.stdout
+
+
+def test_bench_reference_arm_prints_the_contract_line():
+    # `bench.py --impl reference` (the CPU arm the driver runs beside the CUDA arm): one JSON line with the
+    # contract's keys, the unmodified reference when baseline/_ref is present, no GPU touched
+    env = dict(os.environ, CUDA_VISIBLE_DEVICES="")
+    out = subprocess.run([sys.executable, os.path.join(REPO, "bench.py"), "--impl", "reference", "--steps", "1",
+                          "--warmup", "0", "--workload", "cube1000"], capture_output=True, text=True, env=env,
+                         timeout=600, cwd=REPO)
+    assert out.returncode == 0, out.stderr[-2000:]
+    line = json.loads(out.stdout.strip().splitlines()[-1])
+    assert line["impl"] == "reference" and line["metric"] == "mc_chain_steps_per_s" and line["higher_is_better"] is True
+    assert line["value"] > 0 and line["unit"] == "chain-steps/s" and line["n_gpus"] == 1
+    assert line["e2e"]["value"] == line["value"] and line["e2e"]["h2d_bytes_per_step"] == 0
+    base = line["cpu_baseline"]
+    assert base["cores"] >= 1 and base["kind"] in ("reference", "port")
+    if os.path.isfile(os.path.join(REPO, "baseline", "_ref", "mchammer", "__init__.py")):
+        assert base["kind"] == "reference"
