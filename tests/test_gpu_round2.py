@@ -374,3 +374,28 @@ def test_topology_cache_returns_what_a_fresh_lowering_would():
     for k in range(engine._TOPOLOGY_CACHE_SIZE + 3):  # bounded
         engine.cached_topology(n, long_bonds[: 1 + k % len(long_bonds)] * (1 + k // len(long_bonds)), subunits, 0, allow_overlap=True)
     assert len(engine._TOPOLOGY_CACHE) <= engine._TOPOLOGY_CACHE_SIZE
+
+
+def test_long_fp64_chain_keeps_the_reference_sequence():
+    # 3000 steps of poc.mol (six times the reference's own example length): the accept/reject sequence still
+    # equals the oracle's, potentials and positions within 1e-9 -- no drift in the carried energy table, the
+    # coordinate sums or the random stream
+    g = load_golden("poc_graph_seed1000")
+    mol = golden_molecule(g)
+    bonds, subunits = golden_bonds(g), golden_subunits(g)
+    steps, seed = 3000, 77
+    p = orc.OptimizerParams(step_size=0.25, target_bond_length=1.2, num_steps=steps)
+    want = orc.optimizer_run(mol.get_position_matrix(), bonds, subunits, p, np.random.default_rng(seed))
+    opt = mch.Optimizer(0.25, 1.2, steps, random_seed=seed)
+    out_mol, result = opt.get_trajectory(mol, bonds, subunits)
+    props = [q for _, q in result.get_steps_properties()]
+    passed = np.array([-1 if q["passed"] is None else int(q["passed"]) for q in props])
+    assert np.array_equal(passed, want.passed)
+    assert rel_close([q["system_potential"] for q in props], want.system_potential, RTOL64)
+    assert rel_close([q["nonbonded_potential"] for q in props], want.nonbonded_potential, RTOL64)
+    assert np.allclose(out_mol.get_position_matrix(), want.final_positions, rtol=RTOL64, atol=1e-9)
+    # fast mode over the same 3000 steps: the carried potential still equals a fresh evaluation of its own geometry
+    fast = mch.Optimizer(0.25, 1.2, steps, random_seed=seed, precision="fp32")
+    fmol, last = fast.get_result(mol, bonds, subunits)
+    fresh_u, _ = mch.Optimizer(0.25, 1.2, 2).compute_potential(fmol, bonds)
+    assert rel_close(last.system_potential, fresh_u, RTOL32)
