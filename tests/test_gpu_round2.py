@@ -399,3 +399,29 @@ def test_long_fp64_chain_keeps_the_reference_sequence():
     fmol, last = fast.get_result(mol, bonds, subunits)
     fresh_u, _ = mch.Optimizer(0.25, 1.2, 2).compute_potential(fmol, bonds)
     assert rel_close(last.system_potential, fresh_u, RTOL32)
+
+
+@pytest.mark.parametrize("n_per_subunit", [12, 50])
+def test_collapser_decides_at_the_threshold_like_the_reference(n_per_subunit):
+    # The contact pass works in a fast form that cannot resolve 1e-12; every pair it puts near the threshold is
+    # re-evaluated in the plain form (csrc/mch_collapse.cuh).  Thresholds placed a hair above / below the minimum
+    # distance the reference sees after step k must end the collapse at step k / let it run on, exactly like the
+    # oracle -- fp64 decides such cases identically, fp32 within its stated +-1 step.
+    mol, long_bonds, subunits = synthetic.cube_cage(atoms_per_subunit=n_per_subunit, seed=4, spread=7.0, h_fraction=0.25)
+    pos0 = mol.get_position_matrix()
+    is_h = [a.get_element_string() == "H" for a in mol.get_atoms()]
+    step_size, k = 0.03, 6
+    pos = pos0.copy()
+    for _ in range(k):
+        pos = orc.collapser_step(pos, subunits, step_size, True)
+    d_k = orc.min_subunit_distance(pos, is_h, subunits)
+    for factor in (1.0 + 1e-12, 1.0 - 1e-12, 1.0 + 1e-9, 1.0 - 1e-9):
+        thr = d_k * factor
+        want = orc.collapser_run(pos0, is_h, long_bonds, subunits, step_size, thr, True)
+        coll = mch.Collapser(step_size=step_size, distance_threshold=thr, scale_steps=True)
+        got_mol, result = coll.get_trajectory(mol, long_bonds, subunits)
+        assert result.get_step_count() == want.steps_run, (factor, result.get_step_count(), want.steps_run)
+        assert np.allclose(got_mol.get_position_matrix(), want.final_positions, rtol=0, atol=1e-9)
+        fast = mch.Collapser(step_size=step_size, distance_threshold=thr, scale_steps=True, precision="fp32")
+        fmol, fres = fast.get_trajectory(mol, long_bonds, subunits)
+        assert abs(fres.get_step_count() - want.steps_run) <= 1
