@@ -115,3 +115,50 @@ def optimize_batch(states, optimizer, seeds=1000, devices=None):
                 "n_accepted": int(res.n_accepted[slot]),
             })
     return out
+
+
+def collapse_batch(states, collapser):
+    """Collapse many stk-shaped molecules/states in batched launches (NEW; no reference counterpart).
+
+    Per state this is what stk's ``Collapser`` optimizer does with the reference (the wiring of
+    tests/stk_reproduction/test_stk.py:97-135 with ``mch.Collapser`` in place of ``mch.Optimizer``):
+    atoms + sorted bonds -> :class:`Molecule`, ``bond_pair_ids = get_long_bond_ids(state)``,
+    ``subunits = get_subunits(state)``, then ``Collapser(...).get_result(...)``.  States that share a
+    topology (atom count, elements, long bonds, building-block assignment) go to the device as ONE
+    ``Collapser.get_results_batch`` call with per-molecule start geometries.
+
+    Returns a list, in input order, of ``(new_state, record)``; ``record`` holds ``steps_run``,
+    ``min_distance`` (the value the reference tests against ``distance_threshold / 2``) and
+    ``max_bond_distance`` after the last step.
+    """
+    import numpy as np
+
+    states = list(states)
+    groups: dict = {}
+    lowered = []
+    for index, state in enumerate(states):
+        long_bonds = get_long_bond_ids(state)
+        subunits = {k: list(v) for k, v in get_subunits(state).items()}
+        positions = np.asarray(state.get_position_matrix(), dtype=np.float64)
+        elements = tuple(type(a).__name__ for a in state.get_atoms())
+        key = (positions.shape[0], elements, long_bonds, tuple((k, tuple(v)) for k, v in subunits.items()))
+        groups.setdefault(key, []).append(index)
+        lowered.append((long_bonds, subunits, positions))
+    out: list = [None] * len(states)
+    for members in groups.values():
+        first = members[0]
+        long_bonds, subunits, _ = lowered[first]
+        template = molecule_from_stk(states[first])
+        stack = np.stack([lowered[i][2] for i in members])
+        res = collapser.get_results_batch(template, long_bonds, subunits, stack)
+        for slot, index in enumerate(members):
+            final = np.array(res.positions[slot], dtype=np.float64)
+            state = states[index]
+            new_state = (state.with_position_matrix(final) if hasattr(state, "with_position_matrix")
+                         else molecule_from_stk(state).with_position_matrix(final))
+            out[index] = (new_state, {
+                "steps_run": int(res.steps_run[slot]),
+                "min_distance": float(res.min_distance[slot]),
+                "max_bond_distance": float(res.max_bond_distance[slot]),
+            })
+    return out

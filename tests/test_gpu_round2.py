@@ -425,3 +425,33 @@ def test_collapser_decides_at_the_threshold_like_the_reference(n_per_subunit):
         fast = mch.Collapser(step_size=step_size, distance_threshold=thr, scale_steps=True, precision="fp32")
         fmol, fres = fast.get_trajectory(mol, long_bonds, subunits)
         assert abs(fres.get_step_count() - want.steps_run) <= 1
+
+
+def test_stk_collapse_batch_against_oracle():
+    # stk's Collapser optimizer wiring for a small set: three conformers of one topology and one molecule of
+    # another, one call; every molecule must end where the oracle's Collapser puts it
+    rng = np.random.default_rng(12)
+    mol, long_bonds, subunits = synthetic.cube_cage(atoms_per_subunit=8, seed=5, spread=6.5)
+    base = mol.get_position_matrix()
+    owner = np.zeros(base.shape[0], dtype=int)
+    for k, ids in subunits.items():
+        owner[ids] = k
+    intra = [(b.get_atom1_id(), b.get_atom2_id()) for b in mol.get_bonds()]
+    states = [_State(base * s + rng.normal(scale=0.01, size=base.shape), owner, intra, list(long_bonds)) for s in (1.0, 1.1, 1.2)]
+    mol2, lb2, su2 = synthetic.cube_cage(atoms_per_subunit=5, seed=8, spread=6.0)
+    owner2 = np.zeros(mol2.get_num_atoms(), dtype=int)
+    for k, ids in su2.items():
+        owner2[ids] = k
+    states.insert(1, _State(mol2.get_position_matrix(), owner2,
+                            [(b.get_atom1_id(), b.get_atom2_id()) for b in mol2.get_bonds()], list(lb2)))
+    coll = mch.Collapser(step_size=0.05, distance_threshold=1.5, scale_steps=True)
+    results = stk_helpers.collapse_batch(states, coll)
+    assert len(results) == len(states)
+    for state, (new_state, record) in zip(states, results):
+        is_h = [type(a).__name__ == "H" for a in state.get_atoms()]
+        want = orc.collapser_run(state.get_position_matrix(), is_h, stk_helpers.get_long_bond_ids(state),
+                                 dict(stk_helpers.get_subunits(state)), 0.05, 1.5, True)
+        assert isinstance(new_state, _State)
+        assert record["steps_run"] == want.steps_run
+        assert np.allclose(new_state.get_position_matrix(), want.final_positions, rtol=0, atol=1e-9)
+        assert rel_close(record["min_distance"], want.min_distance, RTOL64)
