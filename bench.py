@@ -509,6 +509,16 @@ def cuda_arm(args):
     dev_seconds = sum(kernel_ms) * 1e-3
     pairs_per_launch = int(plan.shards[0].out.pair_evals.sum().item())
     gpu_launches_e2e = len(plan._slices(chains))
+    # in-run validity of what was just timed: the potential every chain CARRIED through its moves against a fresh
+    # float64 all-pairs evaluation (the potential kernel) of the chain's own final geometry
+    from mchammer_b200 import engine as _engine
+    _out = plan.shards[0].out
+    _sample = min(chains, 512)
+    _bdev = torch.tensor(np.asarray(long_bonds, dtype=np.int32).reshape(-1), dtype=torch.int32, device=device)
+    _fresh, _, _ = _engine.potential_on_device(_out.positions[:_sample].to(torch.float64), _bdev, len(long_bonds),
+                                               opt._params(), "fp64")
+    _carried = _out.system_potential[:_sample]
+    carried_vs_fresh = float(((_carried - _fresh).abs() / _fresh.abs()).max().item())
 
     # ---------------- end to end through the public API (host buffers in, host buffers out)
     host_positions = plan.h_pos_in  # pinned [C,N,3]; per-chain start geometries
@@ -579,6 +589,11 @@ def cuda_arm(args):
             "pair_evals_per_s": pairs_per_launch * world / launch_s,
             "reference_equivalent_pair_evals_per_s": value * (n_atoms * (n_atoms - 1) // 2),
             "accepted_moves_per_chain": accepted,
+            "carried_potential_check": {
+                "max_rel_diff": carried_vs_fresh, "chains": min(chains, 512),
+                "what": "after the timed launch: |U carried through all moves - fresh float64 all-pairs potential of the "
+                        "chain's final geometry| / U, max over the sampled chains (tolerance of the fast mode: 1e-4; "
+                        "parity mode: 1e-9)"},
             "roofline": {
                 "bound": "fp32_pipe" if args.precision == "fp32" else "fp64_pipe",
                 "achieved": achieved_tflops, "peak": pipe_peak, "unit": "TFLOP/s",
