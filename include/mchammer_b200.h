@@ -27,6 +27,12 @@ extern "C" {
 #define MCH_F64 0
 #define MCH_F32 1
 
+/* mch_optimize_desc.flags.  EARLY_REJECTION: proposals that a pair-free lower bound of U_new - U already rejects
+ *  are booked by the chain's control warp without a pair sweep -- the same decisions and the same
+ * results as the full evaluation, fewer pair terms.  Honoured for one-CTA chains of 64 / 128 threads with mu = 3
+ * and no per-step records; ignored (full evaluation) otherwise. */
+#define MCH_FLAG_EARLY_REJECTION 1
+
 /* Constructor arguments of Optimizer (reference src/mchammer/_internal/optimizer.py:27-38). */
 typedef struct mch_params {
   double step_size;
@@ -96,7 +102,7 @@ typedef struct mch_optimize_desc {
   int32_t general;
   int32_t n_row_lists;        /* the caller's subunits (n_subunits minus the static group); 0 = lists absent */
   int32_t max_rows;           /* longest row list                                          */
-  int32_t reserved;           /* 0                                                         */
+  int32_t flags;              /* 0, or MCH_FLAG_* bits                                     */
   const int32_t* bond_slots;  /* [dev] [n_bonds][2] slot of each bond end                  */
   const int32_t* row_offsets; /* [dev] [n_row_lists + 1]                                   */
   const int32_t* row_slots;   /* [dev] slots of the atoms each subunit lists, ascending, each once */

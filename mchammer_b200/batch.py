@@ -131,7 +131,8 @@ class BatchPlan:
 
     def __init__(self, topo: LoweredTopology, base_positions: np.ndarray, params, num_steps: int,
                  precision: str, n_chains: int, devices: Sequence[int], io_dtype=np.float64,
-                 per_chain_positions: bool = False, threads_per_chain: int = 0, n_slices: int = 0):
+                 per_chain_positions: bool = False, threads_per_chain: int = 0, n_slices: int = 0,
+                 early_reject: bool | None = None):
         torch = native.require_cuda()
         native.lib()
         self._torch = torch
@@ -141,6 +142,8 @@ class BatchPlan:
         self.precision = precision
         self.n_chains = int(n_chains)
         self.threads_per_chain = int(threads_per_chain)
+        # None: the precision mode's default (engine.resolve_early_reject); never changes a result
+        self.early_reject = early_reject
         self.per_chain_positions = bool(per_chain_positions)
         # `run` cuts every device's chains into slices and pipelines H2D / kernel / D2H of
         # consecutive slices on side streams (0 = choose: 4 slices once the copies are worth hiding)
@@ -211,6 +214,7 @@ class BatchPlan:
                 sh.out = engine.optimize_on_device(
                     sh.dtopo, sh.pos_in, sh.count, sh.rng, self.params, self.num_steps,
                     self.precision, threads_per_chain=self.threads_per_chain, out=sh.out,
+                    early_reject=self.early_reject,
                 )
 
     def download(self) -> int:
@@ -275,6 +279,7 @@ class BatchPlan:
                             sh.dtopo, pos, hi - lo, sh.rng[lo:hi], self.params, self.num_steps,
                             self.precision, threads_per_chain=self.threads_per_chain, out=sh.out_slice(lo, hi),
                             resident_chains_hint=sh.count,  # the slices run concurrently: choices are the batch's
+                            early_reject=self.early_reject,
                         )
                         self.h_pos_out[g_lo:g_hi].copy_(o.positions, non_blocking=True)
                         self.h_f64[0, g_lo:g_hi].copy_(o.system_potential, non_blocking=True)

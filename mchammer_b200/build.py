@@ -30,6 +30,12 @@ HEADERS = [
     os.path.join("..", "..", "include", "mchammer_b200.h"),
 ]
 
+# The step kernel exists in two instantiations that must agree bit for bit (full evaluation / early rejection,
+# csrc/mch_optimize.cuh).  Implicit contraction of a * b + c into an FMA is the compiler's choice per instantiation
+# (it was observed to differ: last-bit differences in the carried potentials), so these translation units are
+# compiled without it; every FMA of the pair sweeps is written out (fma(), packed-instruction asm) and stays.
+PER_SOURCE_FLAGS = {"mch_optimize_f32.cu": ["-fmad=false"], "mch_optimize_f64.cu": ["-fmad=false"]}
+
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-lineinfo", "-O3", "-std=c++17",
@@ -68,7 +74,8 @@ def build_library(force: bool = False, verbose: bool = False, defines=(), out: s
     jobs = []
     for src in SOURCES:
         obj = os.path.join(objdir, os.path.splitext(src)[0] + ".o")
-        cmd = [_nvcc(), *NVCC_FLAGS, *[f"-D{d}" for d in defines], "-c", "-o", obj, os.path.join(CSRC, src)]
+        cmd = [_nvcc(), *NVCC_FLAGS, *PER_SOURCE_FLAGS.get(src, []), *[f"-D{d}" for d in defines], "-c", "-o", obj,
+               os.path.join(CSRC, src)]
         if verbose:
             cmd[1:1] = ["-Xptxas", "-v"]
         jobs.append((cmd, obj, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))

@@ -326,6 +326,14 @@ int mch_optimize_batch(const mch_optimize_desc* d, void* stream) {
   a.defer = defer;
   a.cluster = cluster;
   a.regs64 = regs64 ? 1 : 0;
+  // early rejection (opt-in, MCH_FLAG_EARLY_REJECTION): one-CTA chains of 64 / 128 threads that defer their control
+  // work and regroup with one warp (subunits of up to 64 atoms), mu = 3, no per-step records
+  a.early = ((d->flags & MCH_FLAG_EARLY_REJECTION) && cluster == 1 && !regs64 && defer && mk == mch::MU_3 &&
+             d->max_subunit_atoms <= mch::REGROUP_SMALL && (threads == 64 || threads == 128) &&
+             !(d->compute_dtype == MCH_F64 && threads == 64) &&
+             !(d->compute_dtype == MCH_F32 && d->inexact_undo) &&  // fp32 undo: positions drift by whole fp32 ulps
+             !d->trace_potentials && !d->trace_info && !d->trajectory && d->params.beta > 0.0 &&
+             d->params.nonbond_epsilon >= 0.0 && d->params.nonbond_sigma >= 0.0) ? 1 : 0;
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
   const bool io_f64 = d->io_dtype == MCH_F64;
   return d->compute_dtype == MCH_F64 ? mch::launch_optimize_f64(io_f64, mk, a, threads, smem, s)

@@ -66,6 +66,11 @@ int launch_optimize_f64(bool io_f64, int mu_kind, const OptArgs& a, int threads,
 
 template <typename T, typename Tio, int NTMAX>
 int launch_optimize_nt(int mk, const OptArgs& a, int threads, int smem, cudaStream_t s) {
+  // the EARLY instantiation (mch_optimize.cuh): the host sets a.early only for what is instantiated here
+  if constexpr (NTMAX == 64 || NTMAX == 128) {
+    if (a.early && mk == MU_3)
+      return launch(mch_optimize_kernel<T, Tio, MU_3, NTMAX, false, true>, a, a.C, threads, smem, s, "mch_optimize_batch");
+  }
 #ifdef MCH_QUICK  // tuning builds (profiles/quick_variant.sh): mu = 3 only, seconds instead of minutes
   if (mk != MU_3) return fail(-3, "MCH_QUICK build: mu = 3 only");
   return launch(mch_optimize_kernel<T, Tio, MU_3, NTMAX>, a, a.C, threads, smem, s, "mch_optimize_batch");

@@ -78,6 +78,7 @@ struct OptArgs {
   int defer;                 // 1: deferred control work + second column-sum buffer (see header)
   int cluster;               // CTAs per chain (thread-block cluster; 1 = the chain is one CTA)
   int regs64;                // 1: the host wants the 64-register (1024-thread) fp32 instantiation: two 512-thread chains per SM
+  int early;                 // 1: the EARLY instantiation (proposals that a pair-free bound rejects never wake the sweep)
 };
 
 struct Ctl {
@@ -95,11 +96,12 @@ struct Ctl {
   double tv[3];
   unsigned rng_has32, rng_half;
   int kb, kind, n_acc, info, d_accepted, d_ms, d_buf, d_step, cur_ms;
+  int next_step;             // EARLY instantiation: the step whose sweep follows the next barrier A
 };
 
 // Shared-memory carve-up, identical on host (size query) and device.
 struct OptLayout {
-  int x, y, z, colsum, colsum_stride, rows, E, erow, csum, invn, wsum, xsum, epart, suoff, bslot, bsu, ctl, rc, total;
+  int x, y, z, colsum, colsum_stride, rows, E, erow, csum, invn, wsum, xsum, epart, suoff, bslot, bsu, ctl, rc, rad, total;
 };
 
 MCH_HD int align_up(int v, int a) { return (v + a - 1) / a * a; }
@@ -137,6 +139,8 @@ MCH_HD OptLayout opt_layout(int N, int S, int B, int max_su, int tsize, int defe
 #ifdef MCH_RACECHECK  // shadows of the locations other CTAs of the cluster touch: xsum, epart, E (8 bytes each)
   o += cluster > 1 ? (2 * kMaxCluster + 2 * kMaxCluster * S + S * S) * 8 : 0;
 #endif
+  o = align_up(o, 8);
+  L.rad = o; o += S * 4;  // subunit radii, fp32 (EARLY instantiation)
   L.total = align_up(o, 16);
   return L;
 }
@@ -221,9 +225,13 @@ template <typename T, int NTMAX> constexpr int min_blocks_per_sm() {
 // -- same inputs, same arithmetic, same decisions -- and only the sweep's columns are split; what the
 // CTAs exchange through distributed shared memory, one cluster barrier per step, is the per-CTA sweep
 // total and, after an accept, the per-CTA partial sums of the new energy-table row.
-template <typename T, typename Tio, int MUK, int NTMAX, bool CL = false>
+// EARLY: proposals that a pair-free lower bound of U_new - U rejects are decided by the control warp on the spot --
+// no barrier, no sweep -- and the chain moves on to its next proposal (see propose_next below).  A separate
+// instantiation, so that the default kernel's code is exactly what it was.
+template <typename T, typename Tio, int MUK, int NTMAX, bool CL = false, bool EARLY = false>
 __global__ void __launch_bounds__(NTMAX, (min_blocks_per_sm<T, NTMAX>()))
 mch_optimize_kernel(const __grid_constant__ OptArgs a) {
+  static_assert(!(EARLY && CL), "early rejection: one-CTA chains only");
   extern __shared__ __align__(32) unsigned char smem[];
   const int G = CL ? a.cluster : 1;                  // CTAs of this chain
   const int c = CL ? (int)blockIdx.x / G : (int)blockIdx.x;
@@ -468,7 +476,7 @@ mch_optimize_kernel(const __grid_constant__ OptArgs a) {
   // vector, the displaced rows Q and the sweep descriptor.  The other warps are waiting at
   // barrier A while this runs; everything that is not needed to START the sweep (bond
   // energies of the trial geometry, energy-table refresh, trace) is done in `deferred`.
-  auto propose = [&](int buf) {
+  auto draw_move = [&]() {
     kb = (int)pcg_bounded(rng, (uint32_t)B);                       // :214
     const int sa = bslot[2 * kb], sb = bslot[2 * kb + 1];
     const double bvx = (double)X[sb] - (double)X[sa];              // :215-217 (P[b1] - P[b0])
@@ -502,6 +510,8 @@ mch_optimize_kernel(const __grid_constant__ OptArgs a) {
     tvx = (T)vx; tvy = (T)vy; tvz = (T)vz;
     MCH_CHECK(kb >= 0 && kb < B && ms >= 0 && ms < S, "bond / subunit index of the proposal");
     MCH_CHECK(sa >= 0 && sa < N && sb >= 0 && sb < N, "slot of a bond end");
+  };
+  auto publish_move = [&](int buf) {
     const int n = fill_rows(ms, tvx, tvy, tvz);                    // :248-252  (pos - vector)
     MCH_CHECK(n + 3 <= a.max_su + kRowSlack, "row buffer capacity (padded rows + prefetch overrun)");
     MCH_CHECK(suoff[ms] >= 0 && suoff[ms] <= suoff[ms + 1] && suoff[ms + 1] <= N, "slot range of the moving subunit");
@@ -509,6 +519,85 @@ mch_optimize_kernel(const __grid_constant__ OptArgs a) {
       ctl->nrows = n; ctl->c0 = 0; ctl->g0 = suoff[ms]; ctl->g1 = suoff[ms + 1]; ctl->c1 = N; ctl->ms = ms;
       ctl->buf = kTwoBuf ? buf : 0;
     }
+  };
+  auto propose = [&](int buf) { draw_move(); publish_move(buf); };
+  // ---------------------------------------------------------------- early rejection (EARLY instantiation)
+  // A move is rejected iff U_new >= U and exp(-beta (U_new - U)) <= r, r the next double of the chain's random
+  // stream (mc_operations.py:46-52) -- i.e. iff  dU = U_new - U >= -ln(r) / beta.  r can be read ahead (the
+  // generator is advanced past it only once the draw is certain to happen), and dU has a lower bound that costs
+  // no pair evaluation:
+  //   dU >= - sum_t E[ms][t] (1 - f_t)  +  (bond energy of the trial geometry - current bond energy),
+  //   f_t = (1 + |tv| / d_t)^-mu,   d_t <= every current distance between an atom of ms and an atom of subunit t
+  // (distance of the centroids minus the two subunit radii; rigid subunits: the radii are constants): a
+  // translation by tv lengthens no distance by more than |tv|, so r'^-mu >= r^-mu (1 + |tv| / r)^-mu >= r^-mu f_t
+  // for every pair.  When the bound, less an allowance for every rounding on the way (below), reaches the threshold
+  // (taken from above), the move IS rejected whatever its sweep would add up to.  The control warp then consumes the
+  // draw, books the rejection (fp64: the reference's inexact undo) and proposes the next move at once: the other
+  // warps stay at barrier A, no rows are encoded, no sweep is started.  Decisions and results are those of the full
+  // evaluation, bit for bit (a move that is accepted always gets its full sweep).  Not after an accepted move: the
+  // energy table's new row is rebuilt under the NEXT sweep (deferred), so the proposal that follows an accept is
+  // always swept.
+  // The bound is a sufficient condition only, so it is formed in fp32 in both precision modes (it sits on the chain's
+  // critical path).  Allowance: 1e-4 of sum_t E[ms][t] (the fp32 sweep reproduces the carried table entries to ~1e-6;
+  // the fp32 arithmetic here adds ~3e-6 per term), 1e-5-scaled first-order error terms of the bond part (lengths
+  // to ~4e-7 relative), 1e-9 of the bond energy and 1e-12 of U for the fp64 roundings of the carried potentials
+  // (fp64 mode: the sub-ulp drift of inexactly undone atoms), 1e-5 / 1e-4 A on every radius.
+  float* radf = reinterpret_cast<float*>(smem + L.rad);  // radius of every subunit about its centroid, from above
+  const float inv_beta_up = EARLY ? __double2float_ru(1.0 / a.p.beta) * (1.0f + 1.0e-6f) : 0.0f;
+  auto subunit_radius = [&](int s2) {  // warp 0
+    const double cx = csum[3 * s2] * invn[s2], cy = csum[3 * s2 + 1] * invn[s2], cz = csum[3 * s2 + 2] * invn[s2];
+    float m = 0.0f;
+    for (int i = suoff[s2] + lane; i < suoff[s2 + 1]; i += 32) {
+      const float dx = (float)((double)X[i] - cx), dy = (float)((double)Y[i] - cy), dz = (float)((double)Z[i] - cz);
+      m = fmaxf(m, dx * dx + dy * dy + dz * dz);
+    }
+    m = warp_max_f(m);
+    if (lane == 0) radf[s2] = sqrtf(m) * (1.0f + 1.0e-5f) + 1.0e-4f;
+  };
+  auto bound_rejects = [&]() -> bool {  // warp 0; the drawn move (ms, tv), energy table current
+    Pcg64 peek = rng;
+    const double r = pcg_double(peek);
+    // -ln(r) / beta from above: r rounded down, the fast logarithm's error (2^-21 absolute near 1, 3 ulp elsewhere)
+    const float thr = ((-__logf(__double2float_rd(r))) * (1.0f + 1.0e-5f) + 2.0e-6f) * inv_beta_up;
+    // bond part: only bonds with exactly one end in ms change; dE = eps (r1 - r0)(r1 + r0 - 2 target), the trial end
+    // formed exactly as bond_terms forms it
+    const int m0 = suoff[ms], m1 = suoff[ms + 1];
+    const float be = (float)a.p.bond_epsilon, tl = (float)a.p.target_bond_length;
+    float dub = 0.0f, slack = 0.0f;
+    for (int b = lane; b < B; b += 32) {
+      const int sa = bslot[2 * b], sb = bslot[2 * b + 1];
+      const bool ma = sa >= m0 && sa < m1, mb = sb >= m0 && sb < m1;
+      if (ma != mb) {
+        const T ax = X[sa], ay = Y[sa], az = Z[sa], bx = X[sb], by = Y[sb], bz = Z[sb];
+        const float ex = (float)(ax - bx), ey = (float)(ay - by), ez = (float)(az - bz);
+        const T axt = ma ? ax - tvx : ax, ayt = ma ? ay - tvy : ay, azt = ma ? az - tvz : az;
+        const T bxt = mb ? bx - tvx : bx, byt = mb ? by - tvy : by, bzt = mb ? bz - tvz : bz;
+        const float fx = (float)(axt - bxt), fy = (float)(ayt - byt), fz = (float)(azt - bzt);
+        const float r0 = sqrtf(ex * ex + ey * ey + ez * ez), r1 = sqrtf(fx * fx + fy * fy + fz * fz);
+        const float dr = r1 - r0, sm = r1 + r0 - 2.0f * tl;
+        dub = fmaf(be * dr, sm, dub);
+        slack = fmaf(fabsf(be) * (fmaxf(r0, r1) + fabsf(tl)), fabsf(sm) + fabsf(dr), slack);
+      }
+    }
+    // non-bonded part: what the table entries of ms can lose at most
+    const float tx = (float)tvx, ty = (float)tvy, tz = (float)tvz;
+    const float tvn = sqrtf(tx * tx + ty * ty + tz * tz) * (1.0f + 1.0e-6f);
+    const double cmx = csum[3 * ms] * invn[ms], cmy = csum[3 * ms + 1] * invn[ms], cmz = csum[3 * ms + 2] * invn[ms];
+    const float rms = radf[ms];
+    float loss = 0.0f;
+    for (int t = lane; t < S; t += 32) {
+      if (t == ms) continue;
+      const float dx = (float)(csum[3 * t] * invn[t] - cmx), dy = (float)(csum[3 * t + 1] * invn[t] - cmy),
+                  dz = (float)(csum[3 * t + 2] * invn[t] - cmz);
+      const float d = sqrtf(dx * dx + dy * dy + dz * dz) * (1.0f - 1.0e-6f) - rms - radf[t];
+      float gone = 1.0f;  // touching or overlapping spheres bound nothing: the whole entry may go
+      if (d > 0.0f) { const float q = __fdividef(d, d + tvn); gone = 1.0f - q * q * q; }
+      loss = fmaf((float)E[ms * S + t], gone, loss);  // an infinite or NaN entry (coincident atoms) poisons the bound: no early decision
+    }
+    dub = warp_sum_f(dub); slack = warp_sum_f(slack); loss = warp_sum_f(loss);
+    const float allowance = 1.0e-4f * fabsf((float)erow[ms]) + 1.0e-5f * slack + 1.0e-7f * loss +
+                            (float)(1.0e-9 * fabs(U - Unb) + 1.0e-12 * (fabs(U) + fabs(Unb)));
+    return dub - loss - allowance >= thr;  // false for NaN
   };
   // exp(x) > r for x <= 0, r in [0, 1): decided by a fast fp32 exponential whenever it is
   // clear of r by more than its own error, by the fp64 exponential otherwise -- the outcome
@@ -518,6 +607,33 @@ mch_optimize_kernel(const __grid_constant__ OptArgs a) {
     const float rf = (float)r;
     if (fabsf(ef - rf) > 2.0e-3f * fmaxf(ef, rf)) return ef > rf;
     return exp(x) > r;
+  };
+
+  // EARLY: draw the move of step `decided + 1`; while the bound rejects it, book the rejection and draw again.  The
+  // first move the bound does not reject is published for the sweep.  Returns the last step decided this way (its
+  // successor is the step whose sweep comes next; a.num_steps - 1 if the chain has run out of steps).  `nbuf`: the
+  // column-sum buffer the next sweep writes.
+  auto propose_next = [&](int decided, int nbuf) -> int {
+    while (decided + 1 < a.num_steps) {
+      draw_move();
+      // after an accept the energy table still waits for the accepted move's row: that proposal is swept
+      if (d_accepted || !bound_rejects()) { publish_move(nbuf); break; }
+      ++decided;                      // step `decided` is over: rejected without a single pair term
+      (void)pcg_double(rng);          // U_new >= U is certain, so the accept test's draw is consumed (mc_operations.py:50)
+      if (a.inexact_undo) {           // reference optimizer.py:273-277, as after a swept rejection
+        const int r0 = suoff[ms], n = suoff[ms + 1] - r0;
+        for (int i = lane; i < n; i += 32) {
+          X[r0 + i] = (X[r0 + i] - tvx) - (-tvx); Y[r0 + i] = (Y[r0 + i] - tvy) - (-tvy); Z[r0 + i] = (Z[r0 + i] - tvz) - (-tvz);
+        }
+        __syncwarp();
+        refresh_csum(ms);
+        __syncwarp();
+        refresh_ctot();
+        __syncwarp();
+      }
+      info = kb | (kind << 17) | (ms << 18);
+    }
+    return decided;
   };
 
   // ---------------------------------------------------------------- step 0: full evaluation
@@ -610,14 +726,25 @@ mch_optimize_kernel(const __grid_constant__ OptArgs a) {
     if (a.num_steps <= 1 && lane == 0 && rank == 0) a.maxd[c] = longest;
     __syncwarp();
     if (a.num_steps > 1) {
-      propose(1);
-      if (!kDefer) { double unused; Ub_trial = bond_terms(ms, tvx, tvy, tvz, unused); }
+      if constexpr (EARLY) {
+        for (int s2 = 0; s2 < S; ++s2) subunit_radius(s2);
+        __syncwarp();
+        const int decided = propose_next(0, 1);
+        if (lane == 0) ctl->next_step = decided + 1;
+      } else {
+        propose(1);
+        if (!kDefer) { double unused; Ub_trial = bond_terms(ms, tvx, tvy, tvz, unused); }
+      }
     }
   }
 
   // ---------------------------------------------------------------- Monte-Carlo steps
   for (int step = 1; step < a.num_steps; ++step) {
     __syncthreads();  // A: move published, positions of step-1 final
+    if constexpr (EARLY) {  // the control warp may have decided several steps since the last sweep
+      step = ctl->next_step;
+      if (step >= a.num_steps) break;
+    }
     if (a.traj && rank == 0) {
       const long long frame = ((long long)c * a.num_steps + (step - 1)) * N * 3;
       for (int n = tid; n < N; n += nt) {
@@ -643,6 +770,7 @@ mch_optimize_kernel(const __grid_constant__ OptArgs a) {
           } else {
             if (!kCoop) regroup(colsum + d_buf * colsum_stride, d_ms, 0);
             refresh_erow();
+            if constexpr (EARLY) subunit_radius(d_ms);
             d_accepted = false;
           }
         }
@@ -738,7 +866,7 @@ mch_optimize_kernel(const __grid_constant__ OptArgs a) {
       }
       __syncwarp();
       info = kb | ((ok ? 1 : 0) << 16) | (kind << 17) | (ms << 18);
-      d_accepted = ok; d_ms = ms; d_buf = kTwoBuf ? (step & 1) : 0; d_step = step;
+      d_accepted = ok; d_ms = ms; d_buf = kTwoBuf ? (EARLY ? ctl->buf : (step & 1)) : 0; d_step = step;
       if (kCoop && lane == 0) { ctl->d_accepted = ok ? 1 : 0; ctl->d_ms = ms; }  // for coop_row after barrier A
       if (!kDefer) {
         if (!kCoop) {
@@ -751,7 +879,10 @@ mch_optimize_kernel(const __grid_constant__ OptArgs a) {
           write_trace(step, longest);
         }
       }
-      if (step + 1 < a.num_steps) {
+      if constexpr (EARLY) {
+        const int decided = propose_next(step, (kTwoBuf ? ctl->buf : 0) ^ 1);
+        if (lane == 0) ctl->next_step = decided + 1;
+      } else if (step + 1 < a.num_steps) {
         propose((step + 1) & 1);
         if (!kDefer) { double unused; Ub_trial = bond_terms(ms, tvx, tvy, tvz, unused); }
       }

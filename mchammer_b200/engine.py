@@ -8,6 +8,7 @@ Everything here raises if CUDA or the library is unavailable -- there is no CPU 
 from __future__ import annotations
 
 import ctypes as C
+import os
 from dataclasses import dataclass
 from typing import Sequence
 
@@ -125,6 +126,10 @@ def cached_topology(n_atoms: int, bond_pair_ids, subunits, device_index: int, el
     return dtopo
 
 
+# default of the `early_reject` option per precision mode (see resolve_early_reject)
+EARLY_REJECT_DEFAULT = {"fp64": True, "fp32": False}
+
+
 @dataclass
 class OptimizeOutput:
     """Device tensors produced by one ``mch_optimize_batch`` launch."""
@@ -140,6 +145,23 @@ class OptimizeOutput:
     trace_potentials: object | None  # [C,steps,3] f64
     trace_info: object | None        # [C,steps] i32
     trajectory: object | None        # [C,steps,N,3] io dtype
+
+
+def resolve_early_reject(early_reject: bool | None, precision: str) -> bool:
+    """Whether a launch asks for early rejection (``MCH_FLAG_EARLY_REJECTION``).
+
+    Early rejection never changes a result -- the library decides a proposal without its pair sweep only when a
+    pair-free lower bound of the energy change already rejects it, and ignores the flag for launches it does not
+    cover (records per step, clusters, mu != 3, large subunits) -- so the choice is one of speed only.  An explicit
+    ``early_reject`` wins; then the environment variable ``MCHAMMER_B200_EARLY`` (``1`` / ``0``); the default is on
+    in the fp64 mode (measured +13 % on the bench workload) and off in the fp32 mode (within 1 % either way).
+    """
+    if early_reject is not None:
+        return bool(early_reject)
+    env = os.environ.get("MCHAMMER_B200_EARLY")
+    if env in ("0", "1"):
+        return env == "1"
+    return EARLY_REJECT_DEFAULT[precision]
 
 
 def optimize_on_device(
@@ -158,6 +180,7 @@ def optimize_on_device(
     cluster_size: int = 0,
     resident_chains_hint: int = 0,
     force_split_state: bool = False,
+    early_reject: bool | None = None,
 ) -> OptimizeOutput:
     """Launch the resident Metropolis kernel for ``n_chains`` chains (asynchronous)."""
     torch = native.require_cuda()
@@ -226,7 +249,8 @@ def optimize_on_device(
         # explicit moving sets: needed for overlapping subunits (general = 1) and used by the library on
         # its own for molecules that do not fit one CTA; general = 2 forces the split-state kernel
         desc.general = 2 if force_split_state else (1 if topo.general else 0)
-        desc.n_row_lists, desc.max_rows, desc.reserved = topo.n_user_subunits, topo.max_rows, 0
+        desc.n_row_lists, desc.max_rows = topo.n_user_subunits, topo.max_rows
+        desc.flags = native.MCH_FLAG_EARLY_REJECTION if resolve_early_reject(early_reject, precision) else 0
         desc.bond_slots = ptr(dtopo.bond_slots)
         desc.row_offsets, desc.row_slots = ptr(dtopo.row_offsets), ptr(dtopo.row_slots)
         desc.row_weights = ptr(dtopo.row_weights)

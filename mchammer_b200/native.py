@@ -17,6 +17,7 @@ LIB_PATH = os.environ.get("MCHAMMER_B200_LIB") or os.path.join(
 
 MCH_OK = 0
 MCH_F64, MCH_F32 = 0, 1
+MCH_FLAG_EARLY_REJECTION = 1  # mch_optimize_desc.flags
 
 EXPORTS = (
     "mch_optimize_batch", "mch_optimize_smem_bytes", "mch_potential_batch",
@@ -53,7 +54,7 @@ class OptimizeDesc(C.Structure):
         ("last_step_info", C.c_void_p),
         ("trace_potentials", C.c_void_p), ("trace_info", C.c_void_p),
         ("trajectory", C.c_void_p), ("pair_evals", C.c_void_p),
-        ("general", C.c_int32), ("n_row_lists", C.c_int32), ("max_rows", C.c_int32), ("reserved", C.c_int32),
+        ("general", C.c_int32), ("n_row_lists", C.c_int32), ("max_rows", C.c_int32), ("flags", C.c_int32),
         ("bond_slots", C.c_void_p), ("row_offsets", C.c_void_p), ("row_slots", C.c_void_p),
         ("row_weights", C.c_void_p), ("run_offsets", C.c_void_p), ("runs", C.c_void_p),
     ]

@@ -239,6 +239,7 @@ class Optimizer:
         per_chain_positions: bool = False,
         threads_per_chain: int = 0,
         n_slices: int = 0,
+        early_reject: bool | None = None,
     ) -> BatchPlan:
         """Lower the topology once and allocate pinned/device buffers for ``n_chains`` chains.
 
@@ -255,6 +256,7 @@ class Optimizer:
         return BatchPlan(
             topo, mol.get_position_matrix(), self._params(), self._num_steps, self._precision,
             n_chains, list(devices), io_dtype, per_chain_positions, threads_per_chain, n_slices,
+            early_reject,
         )
 
     def get_results_batch(
@@ -268,6 +270,7 @@ class Optimizer:
         devices: Sequence[int] | None = None,
         io_dtype=np.float64,
         threads_per_chain: int = 0,
+        early_reject: bool | None = None,
     ) -> BatchResult:
         """Run many independent chains of the same topology (NEW; no reference counterpart).
 
@@ -276,7 +279,10 @@ class Optimizer:
         ``mol`` itself for every chain.  ``seeds`` default to consecutive integers starting
         at a value drawn from this optimizer's generator.  Chains are split contiguously
         over ``devices`` (default: this optimizer's device); there is no inter-device
-        communication -- results are concatenated on the host.
+        communication -- results are concatenated on the host.  ``early_reject`` (None: the precision
+        mode's default) lets the kernel reject proposals on a pair-free bound of the energy change
+        without their pair sweep; results are the same bits either way (``BatchResult.pair_evals``
+        shows the difference).
         """
         native.require_cuda()
         if positions is not None:
@@ -299,6 +305,7 @@ class Optimizer:
         plan = self.prepare_batch(
             mol, bond_pair_ids, subunits, n_chains, devices, io_dtype,
             per_chain_positions=positions is not None, threads_per_chain=threads_per_chain,
+            early_reject=early_reject,
         )
         return plan.run(seeds=seeds, positions=positions).copy()
 

@@ -7,7 +7,7 @@ set -e
 NAME=$1; WHICH=${2:-both}; shift; shift || true
 D=mchammer_b200; B=$D/build; V=variants/obj_$NAME
 mkdir -p $V variants
-FLAGS="-gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -ftz=true -Xcompiler -fPIC -DMCH_QUICK $*"
+FLAGS="-gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -ftz=true -fmad=false -Xcompiler -fPIC -DMCH_QUICK $*"
 pids=()
 for k in f32 f64; do
   if [ "$WHICH" = both ] || [ "$WHICH" = $k ]; then

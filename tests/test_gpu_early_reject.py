@@ -1,0 +1,139 @@
+"""Early rejection (MCH_FLAG_EARLY_REJECTION): a proposal that a pair-free lower bound of
+U_new - U already rejects is booked without its pair sweep.  The claim under test is that this is invisible in
+the results -- the same accept/reject sequence as the reference (optimizer.py:202-306, mc_operations.py:39-52),
+the same random stream, the same bits in every output -- and only `pair_evals` shrinks.
+"""
+
+from __future__ import annotations
+
+import numpy as np
+import pytest
+
+import mchammer_b200 as mch
+from mchammer_b200 import engine, rngstate, synthetic
+from mchammer_b200.lowering import lower_topology
+from oracle import mch_oracle as orc
+from tests.test_gpu_parity import RTOL64, rel_close
+
+pytestmark = pytest.mark.gpu
+
+FIELDS = ("positions", "system_potential", "nonbonded_potential", "max_bond_distance", "n_accepted",
+          "last_passed", "last_bond_index")
+
+
+def same_bits(a, b):
+    for k in FIELDS:
+        assert np.array_equal(getattr(a, k), getattr(b, k)), k
+
+
+def both_ways(opt, mol, bonds, subunits, seeds, **kw):
+    full = opt.get_results_batch(mol, bonds, subunits, seeds=seeds, early_reject=False, **kw)
+    early = opt.get_results_batch(mol, bonds, subunits, seeds=seeds, early_reject=True, **kw)
+    return full, early
+
+
+@pytest.mark.parametrize("precision,chains", [("fp32", 2048), ("fp64", 1024), ("fp32", 512), ("fp64", 300)])
+def test_early_rejection_gives_the_same_bits_at_bench_size(precision, chains):
+    # BASELINE configs[3] geometry and step count; 64- and 128-thread chains (full and medium batches)
+    mol, long_bonds, subunits = synthetic.cube_cage()
+    opt = mch.Optimizer(0.25, 1.2, 500, precision=precision)
+    full, early = both_ways(opt, mol, long_bonds, subunits, list(range(1000, 1000 + chains)))
+    same_bits(full, early)
+    # every move of the full run is swept: 499 x 50 x 950 pair terms after step 0
+    assert (full.pair_evals == 499_500 + 499 * 47_500).all()
+    saved = 1.0 - early.pair_evals.sum() / full.pair_evals.sum()
+    assert saved > 0.10, f"only {saved:.3f} of the pair terms avoided"
+
+
+def test_early_rejection_leaves_the_random_stream_where_the_full_run_leaves_it():
+    # engine level: the advanced generator states are part of the contract (test_generator_advances_across_calls)
+    import torch
+
+    mol, long_bonds, subunits = synthetic.cube_cage(atoms_per_subunit=12, seed=5, spread=6.5)
+    topo = lower_topology(mol.get_num_atoms(), long_bonds, subunits)
+    dtopo = engine.upload_topology(topo, 0)
+    dev = torch.device("cuda", 0)
+    pos = torch.from_numpy(mol.get_position_matrix()).to(dev)
+    words = rngstate.seed_states(list(range(40, 40 + 96)))
+    for precision in ("fp64", "fp32"):
+        opt = mch.Optimizer(0.3, 1.2, 400, precision=precision)
+        outs = []
+        for early in (False, True):
+            rng = engine.rng_words_to_device(words, dev)
+            outs.append(engine.optimize_on_device(dtopo, pos, 96, rng, opt._params(), 400, precision,
+                                                  threads_per_chain=128, early_reject=early))
+        torch.cuda.synchronize()
+        for k in ("positions", "system_potential", "nonbonded_potential", "n_accepted", "last_step_info", "rng_state"):
+            assert torch.equal(getattr(outs[0], k), getattr(outs[1], k)), (precision, k)
+        assert int(outs[1].pair_evals.sum()) < int(outs[0].pair_evals.sum())
+
+
+@pytest.mark.parametrize("seed", range(10))
+def test_early_rejection_fuzz_same_bits_and_oracle_sequence(seed):
+    # random ragged molecules and parameters (mu = 3: what the early instantiation covers), per-chain start
+    # geometries; fp64 with early rejection must still be the oracle's chain
+    rng = np.random.default_rng(4321 + seed)
+    n = int(rng.integers(40, 400))
+    n_sub = max(2, n // int(rng.integers(6, 40)))  # subunits of ~6 to ~40 atoms (the early instantiation: up to 64)
+    labels = rng.integers(0, n_sub, size=n)
+    members = {k: [int(i) for i in np.flatnonzero(labels == k)] for k in range(n_sub)}
+    subunits = {int(k): v for k, v in members.items() if v}
+    # subunits as compact blobs (jittered grids) so that the centroid-minus-radii distances are often positive
+    centres = rng.normal(scale=float(rng.uniform(6.0, 25.0)), size=(n_sub, 3))
+    pos = np.zeros((n, 3))
+    for k, ids in subunits.items():
+        side = int(np.ceil(len(ids) ** (1 / 3)))
+        grid = np.array([(x, y, z) for x in range(side) for y in range(side) for z in range(side)], dtype=float)
+        pts = 1.5 * grid[rng.permutation(len(grid))[:len(ids)]] + rng.uniform(-0.3, 0.3, size=(len(ids), 3))
+        pos[ids] = centres[k] + pts - pts.mean(axis=0)
+    keys = list(subunits)
+    bonds = []
+    for _ in range(int(rng.integers(1, 12))):
+        ka, kb = rng.choice(keys, size=2, replace=len(keys) < 2)
+        bonds.append((int(rng.choice(subunits[int(ka)])), int(rng.choice(subunits[int(kb)]))))
+    steps = int(rng.integers(50, 400))
+    kwargs = dict(step_size=float(rng.uniform(0.05, 1.5)), target_bond_length=float(rng.uniform(0.8, 3.0)),
+                  num_steps=steps, bond_epsilon=float(rng.choice([0.5, 20.0, 50.0, 500.0])),
+                  nonbond_epsilon=float(rng.choice([0.0, 5.0, 20.0, 200.0])), nonbond_sigma=float(rng.uniform(0.8, 1.6)),
+                  nonbond_mu=3.0, beta=float(rng.choice([0.05, 1.0, 2.0, 10.0, 200.0])))
+    mol = mch.Molecule(atoms=[mch.Atom(i, "C") for i in range(n)], bonds=[], position_matrix=pos)
+    seeds = list(range(10 * seed, 10 * seed + 24))
+    starts = pos[None] + rng.normal(scale=0.05, size=(len(seeds), 1, 3))  # per-chain frames
+    for precision in ("fp64", "fp32"):
+        opt = mch.Optimizer(precision=precision, **kwargs)
+        full, early = both_ways(opt, mol, bonds, subunits, seeds, positions=starts, threads_per_chain=128)
+        same_bits(full, early)
+        if precision == "fp64":
+            want = orc.optimizer_run(starts[3], bonds, subunits, orc.OptimizerParams(**kwargs), np.random.default_rng(seeds[3]))
+            assert int(early.n_accepted[3]) == int((want.passed == 1).sum())
+            assert int(early.last_passed[3]) == int(want.passed[-1])
+            assert rel_close(early.system_potential[3], want.system_potential[-1], RTOL64)
+            assert np.allclose(early.positions[3], want.final_positions, rtol=RTOL64, atol=1e-9)
+
+
+def test_early_rejection_when_nearly_everything_is_rejected():
+    # stiff bonds at low temperature: long runs of proposals are decided without a sweep, up to the last step
+    mol, long_bonds, subunits = synthetic.cube_cage(atoms_per_subunit=20, seed=9, spread=9.0)
+    for precision in ("fp64", "fp32"):
+        for steps in (2, 3, 50, 301):
+            opt = mch.Optimizer(0.25, 5.5, steps, bond_epsilon=5000.0, beta=50.0, precision=precision)
+            full, early = both_ways(opt, mol, long_bonds, subunits, list(range(64)), threads_per_chain=128)
+            same_bits(full, early)
+    assert early.pair_evals.sum() < 0.8 * full.pair_evals.sum()
+
+
+def test_launches_the_early_instantiation_does_not_cover_ignore_the_flag():
+    mol, long_bonds, subunits = synthetic.cube_cage(atoms_per_subunit=16, seed=2, spread=7.0)
+    seeds = list(range(12))
+    # other exponents, per-step records, blocks other than 64 / 128 threads: full evaluation, same pair count
+    for kw, run_kw in ((dict(nonbond_mu=2.5), {}), (dict(nonbond_mu=6.0), {}), ({}, dict(threads_per_chain=256))):
+        opt = mch.Optimizer(0.25, 1.2, 60, **kw)
+        full, early = both_ways(opt, mol, long_bonds, subunits, seeds, **run_kw)
+        same_bits(full, early)
+        assert np.array_equal(full.pair_evals, early.pair_evals)
+    opt = mch.Optimizer(0.25, 1.2, 60)
+    plan = opt.prepare_batch(mol, long_bonds, subunits, len(seeds), early_reject=True)
+    traj = plan.run_trajectories(seeds=seeds, want_positions=False)
+    want = opt.get_results_batch(mol, long_bonds, subunits, seeds=seeds, early_reject=False)
+    assert np.array_equal(traj.final_positions, want.positions)
+    assert np.array_equal(traj.system_potential[:, -1], want.system_potential)

@@ -437,3 +437,15 @@ def test_bench_reference_arm_prints_the_contract_line():
     assert base["cores"] >= 1 and base["kind"] in ("reference", "port")
     if os.path.isfile(os.path.join(REPO, "baseline", "_ref", "mchammer", "__init__.py")):
         assert base["kind"] == "reference"
+
+
+def test_early_rejection_default_policy_and_environment_override(monkeypatch):
+    from mchammer_b200 import engine as _engine
+
+    assert _engine.resolve_early_reject(None, "fp64") is _engine.EARLY_REJECT_DEFAULT["fp64"]
+    assert _engine.resolve_early_reject(None, "fp32") is _engine.EARLY_REJECT_DEFAULT["fp32"]
+    assert _engine.resolve_early_reject(False, "fp64") is False and _engine.resolve_early_reject(True, "fp32") is True
+    monkeypatch.setenv("MCHAMMER_B200_EARLY", "1")
+    assert _engine.resolve_early_reject(None, "fp32") is True
+    monkeypatch.setenv("MCHAMMER_B200_EARLY", "0")
+    assert _engine.resolve_early_reject(None, "fp64") is False and _engine.resolve_early_reject(True, "fp64") is True
