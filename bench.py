@@ -48,6 +48,8 @@ def parse_args():
     ap.add_argument("--chains", type=int, default=0, help="chains per GPU (default: workload's)")
     ap.add_argument("--num-steps", type=int, default=0, help="Optimizer num_steps (default: workload's)")
     ap.add_argument("--threads", type=int, default=0, help="threads per chain (0 = library default)")
+    ap.add_argument("--early-reject", default="auto", choices=["auto", "on", "off"],
+                    help="early rejection in the step kernel (auto = the library's default for the precision mode)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-secondary", action="store_true", help="skip the fp64 / M12L24 / strong-scaling lines")
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="CPU baseline budget per core")
@@ -323,7 +325,7 @@ def secondary_lines(torch, dist, device, world: int, rank: int, flush, main_valu
     from mchammer_b200 import engine, native, rngstate, synthetic
     from mchammer_b200.lowering import lower_topology
 
-    def resident(workload, chains, num_steps, precision, n_timed):
+    def resident(workload, chains, num_steps, precision, n_timed, early=False):
         mol, long_bonds, subunits = build_workload(workload)
         opt = mch.Optimizer(step_size=0.25, target_bond_length=1.2, num_steps=num_steps, precision=precision,
                             device=device.index)
@@ -338,7 +340,7 @@ def secondary_lines(torch, dist, device, world: int, rank: int, flush, main_valu
         def launch():
             rng.copy_(rng0)
             state["out"] = engine.optimize_on_device(dtopo, pos, chains, rng, opt._params(), num_steps, precision,
-                                                     out=state["out"])
+                                                     out=state["out"], early_reject=early)
 
         seconds = time_resident(torch, dist, device, launch, n_timed, flush)
         pairs = int(state["out"].pair_evals.sum().item())
@@ -356,6 +358,23 @@ def secondary_lines(torch, dist, device, world: int, rank: int, flush, main_valu
         "pair_evals_per_s": pairs * world / sec,
         "roofline": {"bound": "fp64_pipe", "achieved": ach, "peak": peak64, "unit": "TFLOP/s",
                      "frac": ach / peak64 if peak64 else None},
+    }
+    # --- early rejection (same results bit for bit, fewer pair terms; the library's default in parity mode): the
+    # roofline lines above / below time the FULL evaluation, these two the same launches with the flag set
+    full_pairs = pairs
+    sec_e, pairs_e, _ = resident("cube1000", chains, num_steps, "fp64", 2, early=True)
+    out["fp64_early_rejection"] = {
+        "workload": out["fp64"]["workload"] + ", MCH_FLAG_EARLY_REJECTION (library default in this mode)",
+        "value": chains * world * (num_steps - 1) / sec_e, "unit": UNIT, "ms_per_launch": 1e3 * sec_e,
+        "pair_terms_vs_full": pairs_e / full_pairs, "speedup_vs_full": sec / sec_e,
+    }
+    sec_e, pairs_e, _ = resident("cube1000", chains, num_steps, "fp32", 3, early=True)
+    out["fp32_early_rejection"] = {
+        "workload": f"cube1000: {chains} chains/GPU x {n_atoms} atoms, num_steps={num_steps}, fast mode, "
+                    "MCH_FLAG_EARLY_REJECTION (opt-in in this mode)",
+        "value": chains * world * (num_steps - 1) / sec_e, "unit": UNIT, "ms_per_launch": 1e3 * sec_e,
+        "pair_terms_vs_full": pairs_e / full_pairs,
+        "speedup_vs_full": (chains * (num_steps - 1) / sec_e) / main_value if main_chains == chains else None,
     }
     # --- M12L24 (BASELINE configs[4]): the FIXED 65,536-chain batch split over the ranks
     # (65,536 on one GPU ... 8192 per GPU on 8; final geometries of one GPU's share: 7.9 GB at N=1)
@@ -476,8 +495,9 @@ def cuda_arm(args):
     n_atoms = mol.get_num_atoms()
     opt = mch.Optimizer(step_size=0.25, target_bond_length=1.2, num_steps=num_steps,
                         precision=args.precision, device=local)
+    early = {"auto": None, "on": True, "off": False}[args.early_reject]
     plan = opt.prepare_batch(mol, long_bonds, subunits, chains, devices=[local],
-                             per_chain_positions=True, threads_per_chain=args.threads)
+                             per_chain_positions=True, threads_per_chain=args.threads, early_reject=early)
     seeds = [1000 + rank * chains + c for c in range(chains)]
     moves = num_steps - 1
 
@@ -585,6 +605,7 @@ def cuda_arm(args):
                 "chains_per_gpu": chains, "num_steps": num_steps, "precision": args.precision,
                 "io_dtype": "f64", "l2": "flushed between timed steps (256 MiB memset, untimed)",
                 "threads_per_chain": args.threads or "auto",
+                "early_rejection": _engine.resolve_early_reject(early, args.precision),
             },
             "pair_evals_per_s": pairs_per_launch * world / launch_s,
             "reference_equivalent_pair_evals_per_s": value * (n_atoms * (n_atoms - 1) // 2),

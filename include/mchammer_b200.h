@@ -28,9 +28,11 @@ extern "C" {
 #define MCH_F32 1
 
 /* mch_optimize_desc.flags.  EARLY_REJECTION: proposals that a pair-free lower bound of U_new - U already rejects
- *  are booked by the chain's control warp without a pair sweep -- the same decisions and the same
- * results as the full evaluation, fewer pair terms.  Honoured for one-CTA chains of 64 / 128 threads with mu = 3
- * and no per-step records; ignored (full evaluation) otherwise. */
+ * (reference test_move, mc_operations.py:39-52, with the next random double read ahead) are booked
+ * by the chain's control warp without a pair sweep -- the same decisions, the same random stream and the same bits
+ * in every output as the full evaluation; only pair_evals shrinks.  Honoured for one-CTA chains of 64 / 128 threads
+ * with mu = 3, subunits of up to 64 atoms, beta > 0, non-negative epsilon / sigma and no per-step records;
+ * ignored (full evaluation) otherwise. */
 #define MCH_FLAG_EARLY_REJECTION 1
 
 /* Constructor arguments of Optimizer (reference src/mchammer/_internal/optimizer.py:27-38). */

@@ -49,6 +49,18 @@
 #define MCH_RC_PARITY(step) ((step) & 1)
 #endif
 
+// pairs of column units the control warp of a two-warp fp32 chain sweeps less than its share in the EARLY
+// instantiation (see the sweep call in the step loop; measured: profiles/r02_ab_early_handicap.txt)
+// 1: the deferred control work is shared -- warp 1 forms the bond energy of the trial geometry under the sweep,
+// warp 0 keeps the energy-table refresh and the records (see the step loop).  Measured and not taken
+// (profiles/r02_ab_split_deferred.txt: fp32 6.61e7 -> 6.47e7, fp64 2.89e7 -> 2.83e7): default 0.
+#ifndef MCH_SPLIT_D
+#define MCH_SPLIT_D 0
+#endif
+#ifndef MCH_EARLY_HANDICAP
+#define MCH_EARLY_HANDICAP 1
+#endif
+
 namespace mch {
 
 struct OptArgs {
@@ -97,6 +109,7 @@ struct Ctl {
   unsigned rng_has32, rng_half;
   int kb, kind, n_acc, info, d_accepted, d_ms, d_buf, d_step, cur_ms;
   int next_step;             // EARLY instantiation: the step whose sweep follows the next barrier A
+  double ub_w1;              // bond energy of the trial geometry, formed by warp 1 under the sweep (kSplitD)
 };
 
 // Shared-memory carve-up, identical on host (size query) and device.
@@ -306,6 +319,8 @@ mch_optimize_kernel(const __grid_constant__ OptArgs a) {
   const bool kTwoBuf = kDefer && !(CL && G > 1);  // two column-sum buffers (see opt_layout)
   // re-sum an accepted move's row of E with all warps (coop_row) where warp 0 alone would take long
   const bool kCoop = nwarps > 1 && ((CL && G > 1) || !kDefer || a.max_su > REGROUP_SMALL);
+  // the deferred work is shared between warps 0 and 1 (one-CTA chains of at least two warps)
+  const bool kSplitD = (MCH_SPLIT_D != 0) && kDefer && nwarps > 1 && !(CL && G > 1);
   Pcg64 rng;  // loaded after step 0 (nothing of the control state is live across the step-0 sweeps)
   rng.hi = rng.lo = rng.inc_hi = rng.inc_lo = 0ULL; rng.has32 = rng.half = 0u;
   double U = 0.0, Unb = 0.0, Ub_trial = 0.0;
@@ -518,6 +533,7 @@ mch_optimize_kernel(const __grid_constant__ OptArgs a) {
     if (lane == 0) {
       ctl->nrows = n; ctl->c0 = 0; ctl->g0 = suoff[ms]; ctl->g1 = suoff[ms + 1]; ctl->c1 = N; ctl->ms = ms;
       ctl->buf = kTwoBuf ? buf : 0;
+      if (kSplitD) { ctl->tv[0] = (double)tvx; ctl->tv[1] = (double)tvy; ctl->tv[2] = (double)tvz; }  // for warp 1
     }
   };
   auto propose = [&](int buf) { draw_move(); publish_move(buf); };
@@ -555,10 +571,8 @@ mch_optimize_kernel(const __grid_constant__ OptArgs a) {
     if (lane == 0) radf[s2] = sqrtf(m) * (1.0f + 1.0e-5f) + 1.0e-4f;
   };
   auto bound_rejects = [&]() -> bool {  // warp 0; the drawn move (ms, tv), energy table current
-    Pcg64 peek = rng;
-    const double r = pcg_double(peek);
-    // -ln(r) / beta from above: r rounded down, the fast logarithm's error (2^-21 absolute near 1, 3 ulp elsewhere)
-    const float thr = ((-__logf(__double2float_rd(r))) * (1.0f + 1.0e-5f) + 2.0e-6f) * inv_beta_up;
+    // Staged, cheapest first -- every stage can only say "no early decision" (always safe): the bound is at most the
+    // bond part, so a move that does not raise the bond energy, or raises it by less than the threshold, is swept.
     // bond part: only bonds with exactly one end in ms change; dE = eps (r1 - r0)(r1 + r0 - 2 target), the trial end
     // formed exactly as bond_terms forms it
     const int m0 = suoff[ms], m1 = suoff[ms + 1];
@@ -579,6 +593,13 @@ mch_optimize_kernel(const __grid_constant__ OptArgs a) {
         slack = fmaf(fabsf(be) * (fmaxf(r0, r1) + fabsf(tl)), fabsf(sm) + fabsf(dr), slack);
       }
     }
+    dub = warp_sum_f(dub); slack = warp_sum_f(slack);
+    if (!(dub > 0.0f)) return false;
+    Pcg64 peek = rng;
+    const double r = pcg_double(peek);
+    // -ln(r) / beta from above: r rounded down, the fast logarithm's error (2^-21 absolute near 1, 3 ulp elsewhere)
+    const float thr = ((-__logf(__double2float_rd(r))) * (1.0f + 1.0e-5f) + 2.0e-6f) * inv_beta_up;
+    if (!(dub >= thr)) return false;
     // non-bonded part: what the table entries of ms can lose at most
     const float tx = (float)tvx, ty = (float)tvy, tz = (float)tvz;
     const float tvn = sqrtf(tx * tx + ty * ty + tz * tz) * (1.0f + 1.0e-6f);
@@ -594,7 +615,7 @@ mch_optimize_kernel(const __grid_constant__ OptArgs a) {
       if (d > 0.0f) { const float q = __fdividef(d, d + tvn); gone = 1.0f - q * q * q; }
       loss = fmaf((float)E[ms * S + t], gone, loss);  // an infinite or NaN entry (coincident atoms) poisons the bound: no early decision
     }
-    dub = warp_sum_f(dub); slack = warp_sum_f(slack); loss = warp_sum_f(loss);
+    loss = warp_sum_f(loss);
     const float allowance = 1.0e-4f * fabsf((float)erow[ms]) + 1.0e-5f * slack + 1.0e-7f * loss +
                             (float)(1.0e-9 * fabs(U - Unb) + 1.0e-12 * (fabs(U) + fabs(Unb)));
     return dub - loss - allowance >= thr;  // false for NaN
@@ -779,20 +800,28 @@ mch_optimize_kernel(const __grid_constant__ OptArgs a) {
           if (a.trace_f) (void)bond_terms(-1, (T)0, (T)0, (T)0, longest);
           write_trace(d_step, longest);
         }
-        double unused;
-        Ub_trial = bond_terms(ms, tvx, tvy, tvz, unused);
+        if (!kSplitD) {
+          double unused;
+          Ub_trial = bond_terms(ms, tvx, tvy, tvz, unused);
+        }
       } else if (kCoop && d_accepted) {
         refresh_erow();
         d_accepted = false;
       }
       park();
+    } else if (kSplitD && warp == 1) {
+      // warp 1's share of the deferred work: the bond energy of the published trial geometry (read after barrier B)
+      double unused;
+      const double ub = bond_terms(ctl->ms, (T)ctl->tv[0], (T)ctl->tv[1], (T)ctl->tv[2], unused);
+      if (lane == 0) ctl->ub_w1 = ub;
     }
     {
       Cols others{ctl->c0, ctl->g0, ctl->g1, ctl->c1};
       const Centre<T> ctr{(T)ctl->cx, (T)ctl->cy, (T)ctl->cz};
       // warp 0 spends roughly the time of 100 rows x 32 columns on the deferred control work:
       // one pair of column units less for subunits of up to ~50 atoms, nothing for large ones
-      const int handicap = kDefer ? min(1, 50 / ctl->nrows) : 0;
+      constexpr int kHandicap = (EARLY && sizeof(T) == 4) ? MCH_EARLY_HANDICAP : 1;
+      const int handicap = kDefer ? min(kHandicap, kHandicap * 50 / ctl->nrows) : 0;
       double part = pair_sweep<T, MUK, false, true, kXF, kX2, kRot3>(Q, ctl->nrows, X, Y, Z, colsum + ctl->buf * colsum_stride, others, term, ctr, handicap, rank, G);
       part = warp_sum(part);
       if (lane == 0) wsum[warp] = part;
@@ -816,6 +845,7 @@ mch_optimize_kernel(const __grid_constant__ OptArgs a) {
     }
     if (warp == 0) {
       unpark();
+      if (kSplitD) Ub_trial = ctl->ub_w1;
       double fresh = 0.0;
       if (CL && G > 1) {
         for (int r = 0; r < G; ++r) {
