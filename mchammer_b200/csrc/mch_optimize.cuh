@@ -550,9 +550,10 @@ mch_optimize_kernel(const __grid_constant__ OptArgs a) {
   // (taken from above), the move IS rejected whatever its sweep would add up to.  The control warp then consumes the
   // draw, books the rejection (fp64: the reference's inexact undo) and proposes the next move at once: the other
   // warps stay at barrier A, no rows are encoded, no sweep is started.  Decisions and results are those of the full
-  // evaluation, bit for bit (a move that is accepted always gets its full sweep).  Not after an accepted move: the
-  // energy table's new row is rebuilt under the NEXT sweep (deferred), so the proposal that follows an accept is
-  // always swept.
+  // evaluation, bit for bit (a move that is accepted always gets its full sweep).  After an accepted move of subunit
+  // d_ms the table's new row is still to be rebuilt (under the NEXT sweep, deferred): a proposal for another subunit
+  // takes its one stale entry from the accepted sweep's column sums (bound_rejects), a second move of d_ms itself is
+  // swept.
   // The bound is a sufficient condition only, so it is formed in fp32 in both precision modes (it sits on the chain's
   // critical path).  Allowance: 1e-4 of sum_t E[ms][t] (the fp32 sweep reproduces the carried table entries to ~1e-6;
   // the fp32 arithmetic here adds ~3e-6 per term), 1e-5-scaled first-order error terms of the bond part (lengths
@@ -605,6 +606,14 @@ mch_optimize_kernel(const __grid_constant__ OptArgs a) {
     const float tvn = sqrtf(tx * tx + ty * ty + tz * tz) * (1.0f + 1.0e-6f);
     const double cmx = csum[3 * ms] * invn[ms], cmy = csum[3 * ms + 1] * invn[ms], cmz = csum[3 * ms + 2] * invn[ms];
     const float rms = radf[ms];
+    // after an accepted move of d_ms (its row of the table is rebuilt under the NEXT sweep) the entry between ms and
+    // d_ms is stale: its new value, from above, out of the accepted sweep's column sums over the slots of ms
+    float e_new = 0.0f;
+    if (d_accepted) {
+      const T* cs = colsum + d_buf * colsum_stride;
+      for (int j = m0 + lane; j < m1; j += 32) e_new += (float)cs[j];
+      e_new = warp_sum_f(e_new) * (float)scale * (1.0f + 1.0e-5f);
+    }
     float loss = 0.0f;
     for (int t = lane; t < S; t += 32) {
       if (t == ms) continue;
@@ -613,10 +622,11 @@ mch_optimize_kernel(const __grid_constant__ OptArgs a) {
       const float d = sqrtf(dx * dx + dy * dy + dz * dz) * (1.0f - 1.0e-6f) - rms - radf[t];
       float gone = 1.0f;  // touching or overlapping spheres bound nothing: the whole entry may go
       if (d > 0.0f) { const float q = __fdividef(d, d + tvn); gone = 1.0f - q * q * q; }
-      loss = fmaf((float)E[ms * S + t], gone, loss);  // an infinite or NaN entry (coincident atoms) poisons the bound: no early decision
+      const float e = (d_accepted && t == d_ms) ? e_new : (float)E[ms * S + t];
+      loss = fmaf(e, gone, loss);  // an infinite or NaN entry (coincident atoms) poisons the bound: no early decision
     }
     loss = warp_sum_f(loss);
-    const float allowance = 1.0e-4f * fabsf((float)erow[ms]) + 1.0e-5f * slack + 1.0e-7f * loss +
+    const float allowance = 1.0e-4f * (fabsf((float)erow[ms]) + e_new) + 1.0e-5f * slack + 1.0e-7f * loss +
                             (float)(1.0e-9 * fabs(U - Unb) + 1.0e-12 * (fabs(U) + fabs(Unb)));
     return dub - loss - allowance >= thr;  // false for NaN
   };
@@ -637,8 +647,8 @@ mch_optimize_kernel(const __grid_constant__ OptArgs a) {
   auto propose_next = [&](int decided, int nbuf) -> int {
     while (decided + 1 < a.num_steps) {
       draw_move();
-      // after an accept the energy table still waits for the accepted move's row: that proposal is swept
-      if (d_accepted || !bound_rejects()) { publish_move(nbuf); break; }
+      // while the energy table waits for an accepted move's row, a second move of the same subunit is swept
+      if ((d_accepted && ms == d_ms) || !bound_rejects()) { publish_move(nbuf); break; }
       ++decided;                      // step `decided` is over: rejected without a single pair term
       (void)pcg_double(rng);          // U_new >= U is certain, so the accept test's draw is consumed (mc_operations.py:50)
       if (a.inexact_undo) {           // reference optimizer.py:273-277, as after a swept rejection
