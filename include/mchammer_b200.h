@@ -30,8 +30,9 @@ extern "C" {
 /* mch_optimize_desc.flags.  EARLY_REJECTION: proposals that a pair-free lower bound of U_new - U already rejects
  * (reference test_move, mc_operations.py:39-52, with the next random double read ahead) are booked
  * by the chain's control warp without a pair sweep -- the same decisions, the same random stream and the same bits
- * in every output as the full evaluation; only pair_evals shrinks.  Honoured for one-CTA chains of 64 / 128 threads
- * with mu = 3, subunits of up to 64 atoms, beta > 0, non-negative epsilon / sigma and no per-step records;
+ * in every output as the full evaluation; only pair_evals shrinks.  Honoured for one-CTA chains of at least 64
+ * threads (fp64 compute: 128) that defer their control work (the library's choice whenever a second column-sum
+ * buffer costs no resident chain), with mu = 3, beta > 0, non-negative epsilon / sigma and no per-step records;
  * ignored (full evaluation) otherwise. */
 #define MCH_FLAG_EARLY_REJECTION 1
 

@@ -326,12 +326,12 @@ int mch_optimize_batch(const mch_optimize_desc* d, void* stream) {
   a.defer = defer;
   a.cluster = cluster;
   a.regs64 = regs64 ? 1 : 0;
-  // early rejection (opt-in, MCH_FLAG_EARLY_REJECTION): one-CTA chains of 64 / 128 threads that defer their control
-  // work and regroup with one warp (subunits of up to 64 atoms), mu = 3, no per-step records
-  a.early = ((d->flags & MCH_FLAG_EARLY_REJECTION) && cluster == 1 && !regs64 && defer && mk == mch::MU_3 &&
-             d->max_subunit_atoms <= mch::REGROUP_SMALL && (threads == 64 || threads == 128) &&
-             !(d->compute_dtype == MCH_F64 && threads == 64) &&
-             !(d->compute_dtype == MCH_F32 && d->inexact_undo) &&  // fp32 undo: positions drift by whole fp32 ulps
+  // early rejection (opt-in, MCH_FLAG_EARLY_REJECTION): one-CTA chains of at least two warps (fp64: four) that defer
+  // their control work, mu = 3, no per-step records
+  const bool f64c = d->compute_dtype == MCH_F64;
+  a.early = ((d->flags & MCH_FLAG_EARLY_REJECTION) && cluster == 1 && defer && mk == mch::MU_3 &&
+             threads >= (f64c ? 128 : 64) &&
+             !(!f64c && d->inexact_undo) &&  // fp32 undo: positions drift by whole fp32 ulps
              !d->trace_potentials && !d->trace_info && !d->trajectory && d->params.beta > 0.0 &&
              d->params.nonbond_epsilon >= 0.0 && d->params.nonbond_sigma >= 0.0) ? 1 : 0;
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);

@@ -66,11 +66,6 @@ int launch_optimize_f64(bool io_f64, int mu_kind, const OptArgs& a, int threads,
 
 template <typename T, typename Tio, int NTMAX>
 int launch_optimize_nt(int mk, const OptArgs& a, int threads, int smem, cudaStream_t s) {
-  // the EARLY instantiation (mch_optimize.cuh): the host sets a.early only for what is instantiated here
-  if constexpr (NTMAX == 64 || NTMAX == 128) {
-    if (a.early && mk == MU_3)
-      return launch(mch_optimize_kernel<T, Tio, MU_3, NTMAX, false, true>, a, a.C, threads, smem, s, "mch_optimize_batch");
-  }
 #ifdef MCH_QUICK  // tuning builds (profiles/quick_variant.sh): mu = 3 only, seconds instead of minutes
   if (mk != MU_3) return fail(-3, "MCH_QUICK build: mu = 3 only");
   return launch(mch_optimize_kernel<T, Tio, MU_3, NTMAX>, a, a.C, threads, smem, s, "mch_optimize_batch");
@@ -100,9 +95,24 @@ int launch_optimize_cluster(int mk, const OptArgs& a, int threads, int smem, cud
 #endif
 }
 
+// the EARLY instantiations (mch_optimize.cuh; mu = 3, one CTA per chain): the same block-size families as below,
+// 257..512 threads on a 512-thread instantiation of their own (the cluster-capable one has no early form)
+template <typename T, typename Tio>
+int launch_optimize_early(const OptArgs& a, int threads, int smem, cudaStream_t s) {
+  auto go = [&](auto kernel) { return launch(kernel, a, a.C, threads, smem, s, "mch_optimize_batch"); };
+  if constexpr (sizeof(T) == 4) {
+    if (a.regs64 || threads > 512) return go(mch_optimize_kernel<T, Tio, MU_3, 1024, false, true>);
+    if (threads <= 64) return go(mch_optimize_kernel<T, Tio, MU_3, 64, false, true>);
+  }
+  if (threads <= 128) return go(mch_optimize_kernel<T, Tio, MU_3, 128, false, true>);
+  if (threads <= 256) return go(mch_optimize_kernel<T, Tio, MU_3, 256, false, true>);
+  return go(mch_optimize_kernel<T, Tio, MU_3, 512, false, true>);
+}
+
 template <typename T, typename Tio>
 int launch_optimize_io(int mk, const OptArgs& a, int threads, int smem, cudaStream_t s) {
   if (a.cluster > 1) return launch_optimize_cluster<T, Tio>(mk, a, threads, smem, s);
+  if (a.early && mk == MU_3) return launch_optimize_early<T, Tio>(a, threads, smem, s);  // the host sets a.early only for what exists
   // blocks that share an SM with so many others that 128 registers per thread do not fit
   // (a.regs64, set by the host), and blocks of more than 512 threads: the 64-register instantiation
   if constexpr (sizeof(T) == 4) {

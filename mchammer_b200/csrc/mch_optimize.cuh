@@ -786,7 +786,8 @@ mch_optimize_kernel(const __grid_constant__ OptArgs a) {
       }
     }
     if (kCoop && ctl->d_accepted != 0) {  // uniform over the CTA: published by warp 0 before barrier A
-      coop_row(colsum + (kTwoBuf ? ((step - 1) & 1) : 0) * colsum_stride, ctl->d_ms, step & 1);
+      // the accepted sweep's buffer: the previous step's -- EARLY: steps may have been decided since, the buffer is published
+      coop_row(colsum + (kTwoBuf ? (EARLY ? ctl->d_buf : ((step - 1) & 1)) : 0) * colsum_stride, ctl->d_ms, step & 1);
       __syncthreads();
     }
     if (warp == 0) {
@@ -907,7 +908,7 @@ mch_optimize_kernel(const __grid_constant__ OptArgs a) {
       __syncwarp();
       info = kb | ((ok ? 1 : 0) << 16) | (kind << 17) | (ms << 18);
       d_accepted = ok; d_ms = ms; d_buf = kTwoBuf ? (EARLY ? ctl->buf : (step & 1)) : 0; d_step = step;
-      if (kCoop && lane == 0) { ctl->d_accepted = ok ? 1 : 0; ctl->d_ms = ms; }  // for coop_row after barrier A
+      if (kCoop && lane == 0) { ctl->d_accepted = ok ? 1 : 0; ctl->d_ms = ms; ctl->d_buf = d_buf; }  // for coop_row after barrier A
       if (!kDefer) {
         if (!kCoop) {
           if (ok) { regroup(colsum + d_buf * colsum_stride, ms, 0); refresh_erow(); }

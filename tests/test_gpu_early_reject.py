@@ -111,6 +111,49 @@ def test_early_rejection_fuzz_same_bits_and_oracle_sequence(seed):
             assert np.allclose(early.positions[3], want.final_positions, rtol=RTOL64, atol=1e-9)
 
 
+@pytest.mark.parametrize("precision,chains,steps", [("fp32", 300, 40), ("fp32", 80, 100), ("fp64", 80, 100)])
+def test_early_rejection_on_the_m12l24_cage(precision, chains, steps):
+    # BASELINE configs[4] geometry: 208-atom linkers (the accepted row is re-summed by all warps), 512-thread chains
+    # (80 chains: one per SM, too many for the automatic clusters); 300 fp32 chains = two chains per SM = the
+    # 64-register 1024-thread instantiation the full batch runs on
+    mol, long_bonds, subunits = synthetic.cuboctahedron_cage()
+    opt = mch.Optimizer(0.25, 1.2, steps, precision=precision)
+    full, early = both_ways(opt, mol, long_bonds, subunits, list(range(7000, 7000 + chains)))
+    same_bits(full, early)
+    # little to gain here (the linkers' bounding spheres overlap their neighbours', so the bound rarely decides: ~1 %
+    # of the proposals in parity mode; the fast-mode chains of this size do not defer their control work and ignore
+    # the flag) -- what matters is that nothing changes
+    assert early.pair_evals.sum() <= full.pair_evals.sum()
+    if precision == "fp64":
+        assert early.pair_evals.sum() < full.pair_evals.sum()
+
+
+@pytest.mark.parametrize("threads", [64, 128, 256, 512])
+def test_early_rejection_with_large_subunits_at_every_block_size(threads):
+    # 8 subunits of ~110 atoms + 12 of ~25: rows re-summed cooperatively, every early instantiation
+    rng = np.random.default_rng(77)
+    mol, long_bonds, subunits = synthetic.cube_cage(atoms_per_subunit=25, seed=11, spread=10.0)
+    pos = mol.get_position_matrix()
+    extra, owner = [], []
+    for k in range(8):  # grow the eight vertex subunits
+        centre = pos[subunits[k]].mean(axis=0)
+        pts = centre + rng.normal(scale=2.2, size=(85, 3))
+        extra.append(pts); owner += [k] * 85
+    n0 = mol.get_num_atoms()
+    pos2 = np.concatenate([pos] + extra)
+    subunits2 = {k: list(v) for k, v in subunits.items()}
+    for i, k in enumerate(owner):
+        subunits2[k].append(n0 + i)
+    mol2 = mch.Molecule(atoms=[mch.Atom(i, "C") for i in range(len(pos2))], bonds=[], position_matrix=pos2)
+    for precision in ("fp32", "fp64"):
+        if precision == "fp64" and threads < 128:
+            continue
+        opt = mch.Optimizer(0.25, 1.2, 150, precision=precision)
+        full, early = both_ways(opt, mol2, long_bonds, subunits2, list(range(160)), threads_per_chain=threads)
+        same_bits(full, early)
+        assert early.pair_evals.sum() < full.pair_evals.sum()
+
+
 def test_early_rejection_when_nearly_everything_is_rejected():
     # stiff bonds at low temperature: long runs of proposals are decided without a sweep, up to the last step
     mol, long_bonds, subunits = synthetic.cube_cage(atoms_per_subunit=20, seed=9, spread=9.0)
@@ -125,8 +168,8 @@ def test_early_rejection_when_nearly_everything_is_rejected():
 def test_launches_the_early_instantiation_does_not_cover_ignore_the_flag():
     mol, long_bonds, subunits = synthetic.cube_cage(atoms_per_subunit=16, seed=2, spread=7.0)
     seeds = list(range(12))
-    # other exponents, per-step records, blocks other than 64 / 128 threads: full evaluation, same pair count
-    for kw, run_kw in ((dict(nonbond_mu=2.5), {}), (dict(nonbond_mu=6.0), {}), ({}, dict(threads_per_chain=256))):
+    # other exponents, per-step records, one-warp chains, chains on a cluster: full evaluation, same pair count
+    for kw, run_kw in ((dict(nonbond_mu=2.5), {}), (dict(nonbond_mu=6.0), {}), ({}, dict(threads_per_chain=32))):
         opt = mch.Optimizer(0.25, 1.2, 60, **kw)
         full, early = both_ways(opt, mol, long_bonds, subunits, seeds, **run_kw)
         same_bits(full, early)
