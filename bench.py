@@ -367,6 +367,9 @@ def secondary_lines(torch, dist, device, world: int, rank: int, flush, main_valu
         "workload": out["fp64"]["workload"] + ", MCH_FLAG_EARLY_REJECTION (library default in this mode)",
         "value": chains * world * (num_steps - 1) / sec_e, "unit": UNIT, "ms_per_launch": 1e3 * sec_e,
         "pair_terms_vs_full": pairs_e / full_pairs, "speedup_vs_full": sec / sec_e,
+        # what a kernel evaluating EVERY pair term would have to sustain for this rate -- the pair terms of the
+        # reference algorithm per second, most of which this launch never executes; not a pipe utilisation
+        "reference_equivalent_pipe_frac": (FLOPS_PER_PAIR * full_pairs / sec_e / 1e12 / peak64) if peak64 else None,
     }
     sec_e, pairs_e, _ = resident("cube1000", chains, num_steps, "fp32", 3, early=True)
     out["fp32_early_rejection"] = {
