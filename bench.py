@@ -468,6 +468,16 @@ def secondary_lines(torch, dist, device, world: int, rank: int, flush, main_valu
         "value": value, "unit": UNIT, "ms_per_launch": ms, "scaling": "strong",
         "note": "efficiency = value / (n_gpus x the 1-GPU value of this same line)",
     }
+    # the same fixed batch with early rejection (opt-in in fast mode; same results bit for bit)
+    if world == 1 and main_chains == total:
+        value_e, ms_e = out["fp32_early_rejection"]["value"], out["fp32_early_rejection"]["ms_per_launch"]
+    else:
+        sec, _, _ = resident("cube1000", total // world, num_steps, "fp32", 5, early=True)
+        value_e, ms_e = (total // world) * world * (num_steps - 1) / sec, 1e3 * sec
+    out["strong_4096_early_rejection"] = {
+        "workload": out["strong_4096"]["workload"] + ", MCH_FLAG_EARLY_REJECTION",
+        "value": value_e, "unit": UNIT, "ms_per_launch": ms_e, "scaling": "strong",
+    }
     return out
 
 
