@@ -19,14 +19,14 @@ dev = torch.device("cuda", 0)
 out = {}
 
 
-def run(tag, pos, bonds, subunits, steps, precision, cluster, chains, split, threads=0):
+def run(tag, pos, bonds, subunits, steps, precision, cluster, chains, split, threads=0, early=False):
     topo = lower_topology(pos.shape[0], bonds, subunits, allow_overlap=split)
     dtopo = engine.upload_topology(topo, 0)
     rng = engine.rng_words_to_device(rngstate.seed_states(list(range(40, 40 + chains))), dev)
     opt = mch.Optimizer(0.25, 1.2, steps, precision=precision)
     res = engine.optimize_on_device(dtopo, torch.from_numpy(np.ascontiguousarray(pos, dtype=np.float64)).to(dev),
                                     chains, rng, opt._params(), steps, precision, cluster_size=cluster,
-                                    threads_per_chain=threads, force_split_state=split)
+                                    threads_per_chain=threads, force_split_state=split, early_reject=early)
     torch.cuda.synchronize()
     out[tag] = {"n_accepted": res.n_accepted.cpu().tolist(), "U": [float(u).hex() for u in res.system_potential.cpu().tolist()]}
 
@@ -46,4 +46,10 @@ ids = sorted(ss)
 ss[ids[0]] = list(ss[ids[0]]) + list(ss[ids[1]])[:2]  # two atoms listed by two subunits
 for g in (1, 2, 4, 8):
     run(f"overlap fp64 G={g}", small.get_position_matrix(), sb, ss, 60, "fp64", g, 2, True, threads=64)
+# early rejection (csrc/mch_optimize.cuh, EARLY = true): the control warp's loop over decided proposals under the
+# descriptor asserts -- small subunits (one warp regroups) and the 208-atom linkers (all warps re-sum the row)
+big, bb, bs = synthetic.cuboctahedron_cage()
+for precision in ("fp64", "fp32"):
+    run(f"early {precision} cube", pos, bonds, subunits, 120, precision, 1, 160, False, threads=128, early=True)
+    run(f"early {precision} m12l24", big.get_position_matrix(), bb, bs, 40, precision, 1, 80, False, threads=256, early=True)
 print(json.dumps(out))
