@@ -57,6 +57,11 @@
 #ifndef MCH_SPLIT_D
 #define MCH_SPLIT_D 0
 #endif
+// 1: the trial geometry's bond energy is summed through shared memory (one store, B broadcast loads) instead of five
+// dependent shuffle rounds.  Measured and not taken (profiles/r02_ab_bond_smem.txt: fp32 6.60e7 -> 6.55e7): default 0.
+#ifndef MCH_BOND_SMEM
+#define MCH_BOND_SMEM 0
+#endif
 #ifndef MCH_EARLY_HANDICAP
 #define MCH_EARLY_HANDICAP 1
 #endif
@@ -381,7 +386,8 @@ mch_optimize_kernel(const __grid_constant__ OptArgs a) {
     if (lane == 0) { ctot[0] = tx; ctot[1] = ty; ctot[2] = tz; }
   };
   // bond energy sum and longest bond; ends inside subunit `moved` are displaced by -tv
-  auto bond_terms = [&](int moved, T dx, T dy, T dz, double& longest) {
+  // (a warp reduction whose result nobody reads is not dead code to the compiler: say which ones are wanted)
+  auto bond_terms = [&](int moved, T dx, T dy, T dz, double& longest, bool want_sum = true, bool want_longest = true) {
     const int m0 = moved >= 0 ? suoff[moved] : -1, m1 = moved >= 0 ? suoff[moved + 1] : -1;
     double e = 0.0, far = 0.0;
     for (int b = lane; b < B; b += 32) {
@@ -395,8 +401,20 @@ mch_optimize_kernel(const __grid_constant__ OptArgs a) {
       e += a.p.bond_epsilon * (d * d);
       far = fmax(far, r);
     }
-    longest = warp_max(far);
-    return warp_sum(e);
+    if (want_longest) longest = warp_max(far);
+#if MCH_BOND_SMEM
+    // the sum alone, at most one bond per lane: through shared memory (one store, B broadcast loads that pipeline)
+    // instead of five dependent shuffle rounds -- fixed order b = 0 .. B - 1
+    if (want_sum && !want_longest && B <= 32) {
+      wsum[64 + lane] = e;
+      __syncwarp();
+      double s0 = 0.0, s1 = 0.0;
+      for (int b = 0; b < B; b += 2) { s0 += wsum[64 + b]; s1 += wsum[64 + b + 1]; }  // lanes >= B hold 0
+      __syncwarp();
+      return s0 + s1;
+    }
+#endif
+    return want_sum ? warp_sum(e) : 0.0;
   };
   auto write_trace = [&](int step, double longest) {
     if (lane == 0 && rank == 0) {
@@ -572,13 +590,15 @@ mch_optimize_kernel(const __grid_constant__ OptArgs a) {
     if (lane == 0) radf[s2] = sqrtf(m) * (1.0f + 1.0e-5f) + 1.0e-4f;
   };
   auto bound_rejects = [&]() -> bool {  // warp 0; the drawn move (ms, tv), energy table current
-    // Staged, cheapest first -- every stage can only say "no early decision" (always safe): the bound is at most the
-    // bond part, so a move that does not raise the bond energy, or raises it by less than the threshold, is swept.
-    // bond part: only bonds with exactly one end in ms change; dE = eps (r1 - r0)(r1 + r0 - 2 target), the trial end
-    // formed exactly as bond_terms forms it
+    // Everything a lane contributes -- its bonds' energy change less their error terms, less what its table entries
+    // can lose -- goes into ONE lane-local value and one warp reduction: what this section costs on the chain's
+    // critical path is the depth of its dependent shared-memory / shuffle / special-function operations (they queue
+    // behind the sweeping warps' traffic), not its instruction count (profiles/r02_phase_clocks.txt).
     const int m0 = suoff[ms], m1 = suoff[ms + 1];
+    float v = 0.0f;
+    // bond part: only bonds with exactly one end in ms change; dE = eps (r1 - r0)(r1 + r0 - 2 target), the trial end
+    // formed exactly as bond_terms forms it; first-order error terms at 1e-5 (lengths are good to ~4e-7 relative)
     const float be = (float)a.p.bond_epsilon, tl = (float)a.p.target_bond_length;
-    float dub = 0.0f, slack = 0.0f;
     for (int b = lane; b < B; b += 32) {
       const int sa = bslot[2 * b], sb = bslot[2 * b + 1];
       const bool ma = sa >= m0 && sa < m1, mb = sb >= m0 && sb < m1;
@@ -590,45 +610,55 @@ mch_optimize_kernel(const __grid_constant__ OptArgs a) {
         const float fx = (float)(axt - bxt), fy = (float)(ayt - byt), fz = (float)(azt - bzt);
         const float r0 = sqrtf(ex * ex + ey * ey + ez * ez), r1 = sqrtf(fx * fx + fy * fy + fz * fz);
         const float dr = r1 - r0, sm = r1 + r0 - 2.0f * tl;
-        dub = fmaf(be * dr, sm, dub);
-        slack = fmaf(fabsf(be) * (fmaxf(r0, r1) + fabsf(tl)), fabsf(sm) + fabsf(dr), slack);
+        v = fmaf(be * dr, sm, v);
+        v = fmaf(-1.0e-5f * fabsf(be) * (fmaxf(r0, r1) + fabsf(tl)), fabsf(sm) + fabsf(dr), v);
       }
     }
-    dub = warp_sum_f(dub); slack = warp_sum_f(slack);
-    if (!(dub > 0.0f)) return false;
+    // -ln(r) / beta from above: r rounded down, the fast logarithm's error (2^-21 absolute near 1, 3 ulp elsewhere)
     Pcg64 peek = rng;
     const double r = pcg_double(peek);
-    // -ln(r) / beta from above: r rounded down, the fast logarithm's error (2^-21 absolute near 1, 3 ulp elsewhere)
     const float thr = ((-__logf(__double2float_rd(r))) * (1.0f + 1.0e-5f) + 2.0e-6f) * inv_beta_up;
-    if (!(dub >= thr)) return false;
+    // parity mode (four warps per chain, long sweeps, a control section that re-sums coordinates after every
+    // rejection anyway): staged -- the bound is at most the bond part, so a move whose bond part stays below the
+    // threshold is swept without looking at the table (measured: 2.97e7 against 2.94e7 for the one-reduction form;
+    // fast mode the other way round, 6.87e7 against 6.98e7)
+    float bond_part = 0.0f;
+    if (!kFast) {
+      bond_part = warp_sum_f(v);
+      v = 0.0f;
+      if (!(bond_part >= thr)) return false;
+    }
     // non-bonded part: what the table entries of ms can lose at most
     const float tx = (float)tvx, ty = (float)tvy, tz = (float)tvz;
     const float tvn = sqrtf(tx * tx + ty * ty + tz * tz) * (1.0f + 1.0e-6f);
     const double cmx = csum[3 * ms] * invn[ms], cmy = csum[3 * ms + 1] * invn[ms], cmz = csum[3 * ms + 2] * invn[ms];
     const float rms = radf[ms];
-    // after an accepted move of d_ms (its row of the table is rebuilt under the NEXT sweep) the entry between ms and
-    // d_ms is stale: its new value, from above, out of the accepted sweep's column sums over the slots of ms
-    float e_new = 0.0f;
-    if (d_accepted) {
-      const T* cs = colsum + d_buf * colsum_stride;
-      for (int j = m0 + lane; j < m1; j += 32) e_new += (float)cs[j];
-      e_new = warp_sum_f(e_new) * (float)scale * (1.0f + 1.0e-5f);
-    }
-    float loss = 0.0f;
-    for (int t = lane; t < S; t += 32) {
-      if (t == ms) continue;
+    auto may_go = [&](int t) -> float {  // upper bound of 1 - f_t
       const float dx = (float)(csum[3 * t] * invn[t] - cmx), dy = (float)(csum[3 * t + 1] * invn[t] - cmy),
                   dz = (float)(csum[3 * t + 2] * invn[t] - cmz);
       const float d = sqrtf(dx * dx + dy * dy + dz * dz) * (1.0f - 1.0e-6f) - rms - radf[t];
       float gone = 1.0f;  // touching or overlapping spheres bound nothing: the whole entry may go
       if (d > 0.0f) { const float q = __fdividef(d, d + tvn); gone = 1.0f - q * q * q; }
-      const float e = (d_accepted && t == d_ms) ? e_new : (float)E[ms * S + t];
-      loss = fmaf(e, gone, loss);  // an infinite or NaN entry (coincident atoms) poisons the bound: no early decision
+      return gone;
+    };
+    // after an accepted move of d_ms (its row of the table is rebuilt under the NEXT sweep) the entry between ms and
+    // d_ms is stale: its new value is scale * (the accepted sweep's column sums over the slots of ms), taken from
+    // above, lane by lane; 1e-4 of it joins the allowance
+    if (d_accepted) {
+      const T* cs = colsum + d_buf * colsum_stride;
+      float part = 0.0f;
+      for (int j = m0 + lane; j < m1; j += 32) part += (float)cs[j];
+      v = fmaf(-(may_go(d_ms) * (1.0f + 1.0e-5f) + 1.0e-4f) * ((float)scale * (1.0f + 1.0e-6f)), part, v);
     }
-    loss = warp_sum_f(loss);
-    const float allowance = 1.0e-4f * (fabsf((float)erow[ms]) + e_new) + 1.0e-5f * slack + 1.0e-7f * loss +
+    for (int t = lane; t < S; t += 32) {
+      if (t == ms || (d_accepted && t == d_ms)) continue;
+      // an infinite or NaN entry (coincident atoms) poisons the bound: no early decision
+      v = fmaf(-(float)E[ms * S + t] * (1.0f + 1.0e-7f), may_go(t), v);
+    }
+    v = warp_sum_f(v) + bond_part;
+    const float allowance = 1.0e-4f * fabsf((float)erow[ms]) +
                             (float)(1.0e-9 * fabs(U - Unb) + 1.0e-12 * (fabs(U) + fabs(Unb)));
-    return dub - loss - allowance >= thr;  // false for NaN
+    return v - allowance >= thr;  // false for NaN
   };
   // exp(x) > r for x <= 0, r in [0, 1): decided by a fast fp32 exponential whenever it is
   // clear of r by more than its own error, by the fp64 exponential otherwise -- the outcome
@@ -764,14 +794,24 @@ mch_optimize_kernel(const __grid_constant__ OptArgs a) {
         if (lane == 0) ctl->next_step = decided + 1;
       } else {
         propose(1);
-        if (!kDefer) { double unused; Ub_trial = bond_terms(ms, tvx, tvy, tvz, unused); }
+        if (!kDefer) { double unused; Ub_trial = bond_terms(ms, tvx, tvy, tvz, unused, true, false); }
       }
     }
   }
 
+#ifdef MCH_TIMING  // tuning builds only (profiles/phase_clocks.py): where a swept step's cycles go, per warp
+  long long tm_a = 0, tm_d = 0, tm_s = 0, tm_b = 0;               // stamps of the current step
+  long long tm_D = 0, tm_S = 0, tm_W = 0, tm_C = 0, tm_n = 0;     // sums: deferred, own sweep, wait at B, control, swept steps
+#endif
   // ---------------------------------------------------------------- Monte-Carlo steps
   for (int step = 1; step < a.num_steps; ++step) {
+#ifdef MCH_TIMING
+    if (warp == 0 && tm_b != 0) tm_C += clock64() - tm_b;  // barrier B release -> arrival at A
+#endif
     __syncthreads();  // A: move published, positions of step-1 final
+#ifdef MCH_TIMING
+    tm_a = clock64();
+#endif
     if constexpr (EARLY) {  // the control warp may have decided several steps since the last sweep
       step = ctl->next_step;
       if (step >= a.num_steps) break;
@@ -808,12 +848,12 @@ mch_optimize_kernel(const __grid_constant__ OptArgs a) {
         }
         if (d_step > 0 && (a.trace_f || a.trace_i)) {
           double longest = 0.0;
-          if (a.trace_f) (void)bond_terms(-1, (T)0, (T)0, (T)0, longest);
+          if (a.trace_f) (void)bond_terms(-1, (T)0, (T)0, (T)0, longest, false, true);
           write_trace(d_step, longest);
         }
         if (!kSplitD) {
           double unused;
-          Ub_trial = bond_terms(ms, tvx, tvy, tvz, unused);
+          Ub_trial = bond_terms(ms, tvx, tvy, tvz, unused, true, false);
         }
       } else if (kCoop && d_accepted) {
         refresh_erow();
@@ -823,9 +863,12 @@ mch_optimize_kernel(const __grid_constant__ OptArgs a) {
     } else if (kSplitD && warp == 1) {
       // warp 1's share of the deferred work: the bond energy of the published trial geometry (read after barrier B)
       double unused;
-      const double ub = bond_terms(ctl->ms, (T)ctl->tv[0], (T)ctl->tv[1], (T)ctl->tv[2], unused);
+      const double ub = bond_terms(ctl->ms, (T)ctl->tv[0], (T)ctl->tv[1], (T)ctl->tv[2], unused, true, false);
       if (lane == 0) ctl->ub_w1 = ub;
     }
+#ifdef MCH_TIMING
+    tm_d = clock64();
+#endif
     {
       Cols others{ctl->c0, ctl->g0, ctl->g1, ctl->c1};
       const Centre<T> ctr{(T)ctl->cx, (T)ctl->cy, (T)ctl->cz};
@@ -837,7 +880,14 @@ mch_optimize_kernel(const __grid_constant__ OptArgs a) {
       part = warp_sum(part);
       if (lane == 0) wsum[warp] = part;
     }
+#ifdef MCH_TIMING
+    tm_s = clock64();
+#endif
     __syncthreads();  // B: column sums and warp totals published
+#ifdef MCH_TIMING
+    tm_b = clock64();
+    tm_D += tm_d - tm_a; tm_S += tm_s - tm_d; tm_W += tm_b - tm_s; ++tm_n;
+#endif
     if (CL && G > 1) {
       // every CTA of the chain learns every CTA's sweep total (slots double buffered by step parity:
       // a CTA that runs ahead cannot overwrite a slot a slower one still has to read)
@@ -916,7 +966,7 @@ mch_optimize_kernel(const __grid_constant__ OptArgs a) {
         }
         if (step + 1 < a.num_steps && (a.trace_f || a.trace_i)) {
           double longest = 0.0;
-          if (a.trace_f) (void)bond_terms(-1, (T)0, (T)0, (T)0, longest);
+          if (a.trace_f) (void)bond_terms(-1, (T)0, (T)0, (T)0, longest, false, true);
           write_trace(step, longest);
         }
       }
@@ -925,13 +975,13 @@ mch_optimize_kernel(const __grid_constant__ OptArgs a) {
         if (lane == 0) ctl->next_step = decided + 1;
       } else if (step + 1 < a.num_steps) {
         propose((step + 1) & 1);
-        if (!kDefer) { double unused; Ub_trial = bond_terms(ms, tvx, tvy, tvz, unused); }
+        if (!kDefer) { double unused; Ub_trial = bond_terms(ms, tvx, tvy, tvz, unused, true, false); }
       }
     }
   }
   if (warp == 0 && a.num_steps > 1) {  // the last step has no following sweep to hide behind
     double longest;
-    (void)bond_terms(-1, (T)0, (T)0, (T)0, longest);
+    (void)bond_terms(-1, (T)0, (T)0, (T)0, longest, false, true);
     write_trace(a.num_steps - 1, longest);
     if (lane == 0 && rank == 0) a.maxd[c] = longest;
   }
@@ -952,6 +1002,13 @@ mch_optimize_kernel(const __grid_constant__ OptArgs a) {
       store_io<Tio>(a.traj, fr + 0, px); store_io<Tio>(a.traj, fr + 1, py); store_io<Tio>(a.traj, fr + 2, pz);
     }
   }
+#ifdef MCH_TIMING  // the first 12 position values of the chain are overwritten with the cycle sums (warp 0, warp 1)
+  __syncthreads();
+  if (lane == 0 && warp < 2 && rank == 0 && sizeof(Tio) == 8) {
+    double* o = reinterpret_cast<double*>(a.pos_out) + (long long)c * N * 3 + 6 * warp;
+    o[0] = (double)tm_D; o[1] = (double)tm_S; o[2] = (double)tm_W; o[3] = (double)tm_C; o[4] = (double)tm_n; o[5] = 0.0;
+  }
+#endif
   if (warp == 0 && lane == 0) {
     a.U[c] = U; a.Unb[c] = Unb; a.n_accept[c] = n_acc; a.last_info[c] = info;
     if (a.pairs) a.pairs[c] = pair_count;
