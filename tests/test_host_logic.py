@@ -219,6 +219,11 @@ def test_ctypes_structs_match_header_layout(tmp_path):
         assert int(seen[cname]) == CT.sizeof(ctype), cname
         for field, _ in ctype._fields_:
             assert int(seen[f"{cname}.{field}"]) == getattr(ctype, field).offset, (cname, field)
+    # ... and the header's constants against the Python mirror's
+    header = open(os.path.join(REPO, "include", "mchammer_b200.h")).read()
+    for name, value in (("MCH_F64", native.MCH_F64), ("MCH_F32", native.MCH_F32),
+                        ("MCH_FLAG_EARLY_REJECTION", native.MCH_FLAG_EARLY_REJECTION)):
+        assert int(re.search(rf"#define {name} (\d+)", header).group(1)) == value, name
 
 
 def test_c_seeding_matches_numpy():
