@@ -59,6 +59,9 @@
 #endif
 // 1: the trial geometry's bond energy is summed through shared memory (one store, B broadcast loads) instead of five
 // dependent shuffle rounds.  Measured and not taken (profiles/r02_ab_bond_smem.txt: fp32 6.60e7 -> 6.55e7): default 0.
+#ifndef MCH_LAZY_CTOT
+#define MCH_LAZY_CTOT 1
+#endif
 #ifndef MCH_BOND_SMEM
 #define MCH_BOND_SMEM 0
 #endif
@@ -324,6 +327,8 @@ mch_optimize_kernel(const __grid_constant__ OptArgs a) {
   const bool kTwoBuf = kDefer && !(CL && G > 1);  // two column-sum buffers (see opt_layout)
   // re-sum an accepted move's row of E with all warps (coop_row) where warp 0 alone would take long
   const bool kCoop = nwarps > 1 && ((CL && G > 1) || !kDefer || a.max_su > REGROUP_SMALL);
+  // parity mode: the molecule's coordinate sums are re-formed lazily (draw_move), not after every change
+  constexpr int kLazyCtot = kFast ? 0 : MCH_LAZY_CTOT;
   // the deferred work is shared between warps 0 and 1 (one-CTA chains of at least two warps)
   const bool kSplitD = (MCH_SPLIT_D != 0) && kDefer && nwarps > 1 && !(CL && G > 1);
   Pcg64 rng;  // loaded after step 0 (nothing of the control state is live across the step-0 sweeps)
@@ -533,6 +538,9 @@ mch_optimize_kernel(const __grid_constant__ OptArgs a) {
         cvy = csum[3 * ms + 1] * in - ctot[1] * iN;
         cvz = csum[3 * ms + 2] * in - ctot[2] * iN;
       } else {
+        // the molecule's sums are a pure function of the subunit sums (fixed order): formed here, when a centroid
+        // move needs them, instead of after every change of a subunit sum -- the same bits, half as often
+        if (kLazyCtot != 0) { __syncwarp(); refresh_ctot(); __syncwarp(); }
         const double nms = (double)(suoff[ms + 1] - suoff[ms]);
         cvx = csum[3 * ms] / nms - ctot[0] / N;
         cvy = csum[3 * ms + 1] / nms - ctot[1] / N;
@@ -689,8 +697,7 @@ mch_optimize_kernel(const __grid_constant__ OptArgs a) {
         __syncwarp();
         refresh_csum(ms);
         __syncwarp();
-        refresh_ctot();
-        __syncwarp();
+        if (kLazyCtot == 0) { refresh_ctot(); __syncwarp(); }
       }
       info = kb | (kind << 17) | (ms << 18);
     }
@@ -943,7 +950,7 @@ mch_optimize_kernel(const __grid_constant__ OptArgs a) {
         } else {
           refresh_csum(ms);
           __syncwarp();
-          refresh_ctot();
+          if (kLazyCtot == 0) refresh_ctot();
         }
       } else if (a.inexact_undo) {
         // reference optimizer.py:273-277: translate the moved atoms by -tv again
@@ -953,7 +960,7 @@ mch_optimize_kernel(const __grid_constant__ OptArgs a) {
         __syncwarp();
         refresh_csum(ms);
         __syncwarp();
-        refresh_ctot();
+        if (kLazyCtot == 0) refresh_ctot();
       }
       __syncwarp();
       info = kb | ((ok ? 1 : 0) << 16) | (kind << 17) | (ms << 18);
