@@ -381,14 +381,18 @@ mch_optimize_kernel(const __grid_constant__ OptArgs a) {
     const int r0 = suoff[s], r1 = suoff[s + 1];
     double sx = 0.0, sy = 0.0, sz = 0.0;
     for (int i = r0 + lane; i < r1; i += 32) { sx += (double)X[i]; sy += (double)Y[i]; sz += (double)Z[i]; }
-    sx = warp_sum(sx); sy = warp_sum(sy); sz = warp_sum(sz);
-    if (lane == 0) { csum[3 * s] = sx; csum[3 * s + 1] = sy; csum[3 * s + 2] = sz; }
+    warp_sum3(sx, sy, sz, lane);  // totals in lanes 0 / 16 / 8, the bits of three warp_sums
+    if (lane == 0) csum[3 * s] = sx;
+    if (lane == 16) csum[3 * s + 1] = sy;
+    if (lane == 8) csum[3 * s + 2] = sz;
   };
   auto refresh_ctot = [&]() {  // molecule sums = sum of the subunit sums (fixed order)
     double tx = 0.0, ty = 0.0, tz = 0.0;
     for (int s = lane; s < S; s += 32) { tx += csum[3 * s]; ty += csum[3 * s + 1]; tz += csum[3 * s + 2]; }
-    tx = warp_sum(tx); ty = warp_sum(ty); tz = warp_sum(tz);
-    if (lane == 0) { ctot[0] = tx; ctot[1] = ty; ctot[2] = tz; }
+    warp_sum3(tx, ty, tz, lane);
+    if (lane == 0) ctot[0] = tx;
+    if (lane == 16) ctot[1] = ty;
+    if (lane == 8) ctot[2] = tz;
   };
   // bond energy sum and longest bond; ends inside subunit `moved` are displaced by -tv
   // (a warp reduction whose result nobody reads is not dead code to the compiler: say which ones are wanted)
