@@ -154,7 +154,7 @@ def resolve_early_reject(early_reject: bool | None, precision: str) -> bool:
     pair-free lower bound of the energy change already rejects it, and ignores the flag for launches it does not
     cover (records per step, clusters, one-warp chains, mu != 3) -- so the choice is one of speed only.  An explicit
     ``early_reject`` wins; then the environment variable ``MCHAMMER_B200_EARLY`` (``1`` / ``0``); the default is on
-    in the fp64 mode (measured +23 % on the bench workload) and off in the fp32 mode (+5 % for full batches, -3 % at 1024 chains, slower on small batches).
+    in the fp64 mode (measured +24 % on the bench workload) and off in the fp32 mode (+5 % for full batches, -3 % at 1024 chains, slower on small batches).
     """
     if early_reject is not None:
         return bool(early_reject)
