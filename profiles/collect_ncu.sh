@@ -11,8 +11,9 @@ $B > $O/${R}_plain_fp32.json 2> $O/${R}_plain.err &&
 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $O/${R}_launches.csv $B > $O/${R}_ncu_launches.log 2>&1
 $B > /dev/null 2>> $O/${R}_plain.err &&
 ncu --set full --clock-control none --import-source on -k regex:mch_optimize -s 3 -c 1 -f -o $O/${R}_full_fp32 $B > $O/${R}_ncu_full_fp32.log 2>&1
-$B --precision fp64 > /dev/null 2>> $O/${R}_plain.err &&
-ncu --set full --clock-control none --import-source on -k regex:mch_optimize -s 3 -c 1 -f -o $O/${R}_full_fp64 $B --precision fp64 > $O/${R}_ncu_full_fp64.log 2>&1
+# fp64: the full-evaluation kernel (early rejection, the mode's default, has its own captures: ncu_early.sh)
+$B --precision fp64 --early-reject off > /dev/null 2>> $O/${R}_plain.err &&
+ncu --set full --clock-control none --import-source on -k regex:mch_optimize -s 3 -c 1 -f -o $O/${R}_full_fp64 $B --precision fp64 --early-reject off > $O/${R}_ncu_full_fp64.log 2>&1
 python profiles/collapse_batch.py 1184 > $O/${R}_plain_collapse.txt 2>&1 &&
 ncu --set full --clock-control none --import-source on -k regex:mch_collapse -s 1 -c 1 -f -o $O/${R}_full_collapse_fp64 python profiles/collapse_batch.py 1184 > $O/${R}_ncu_collapse.log 2>&1
 python profiles/collapse_batch.py 1184 fp32 > /dev/null 2>&1 &&
